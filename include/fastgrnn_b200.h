@@ -1,0 +1,168 @@
+/*
+ * fastgrnn_b200.h -- C ABI of the B200-native FastGRNN recurrence engine.
+ *
+ * This is the drop-in boundary for the reference's `fastgrnn_cuda` extension:
+ * the four pybind11 entry points of /root/reference/cuda/fastgrnn_cuda.cpp:235-240
+ *
+ *     forward          cuda/fastgrnn_cuda.cpp:73-107   -> fgrnn_forward  (T == 1)
+ *     backward         cuda/fastgrnn_cuda.cpp:109-145  -> fgrnn_backward (T == 1)
+ *     forward_unroll   cuda/fastgrnn_cuda.cpp:147-180  -> fgrnn_forward
+ *     backward_unroll  cuda/fastgrnn_cuda.cpp:182-232  -> fgrnn_backward
+ *
+ * and for the Python unroller they sit under (rnn.py:574-668 BaseRNN.forward,
+ * rnn.py:273-297 FastGRNNCell.forward).  The reference passes torch::Tensor
+ * objects and allocates its outputs; this ABI is plain C: raw device pointers,
+ * sizes, element strides and enums, an explicit CUDA stream, integer return
+ * codes.  The caller allocates every output and the workspace; the library
+ * allocates nothing, keeps no per-call state and never synchronises the host.
+ *
+ * Conventions
+ *   - all matrices are fp32; `x` may be fp32 or bf16 (x_dtype); state is fp32.
+ *   - strides are in ELEMENTS; the innermost (feature / hidden) stride is 1.
+ *     (T,B,F), (B,T,F) and permuted views are all expressed by (stride_b, stride_t).
+ *   - weight_layout selects the reference's two parameter layouts:
+ *       FGRNN_LAYOUT_IH : FastGRNNCell   (rnn.py:246-256)  W[I,H]  U[H,H]  W1[I,rW] W2[rW,H] U1[H,rU] U2[rU,H],  pre = x.W  + h.U
+ *       FGRNN_LAYOUT_HI : FastGRNNCUDA   (rnn.py:782-805)  W[H,I]  U[H,H]  W1[rW,I] W2[H,rW] U1[rU,H] U2[H,rU],  pre = x.W^T + h.U^T
+ *     rW == 0 / rU == 0 selects the full-rank W / U (the reference tests w1.size(0)==0,
+ *     cuda/fastgrnn_cuda.cpp:88-99).  Gradients are written in the same layout.
+ *   - nonlinearity enums 0..2 are the reference's {"sigmoid":0,"relu":1,"tanh":2}
+ *     (rnn.py:478, rnn.py:751); 3..5 are the remaining gen_nonlinearity names (rnn.py:53-60).
+ *   - math (rnn.py:289-295):  pre = wComp + uComp;  z = gate(pre + bias_gate);
+ *     c = update(pre + bias_update);  h' = z*h + (sigmoid(zeta)*(1-z) + sigmoid(nu))*c.
+ *     Backward follows cuda/fastgrnn_cuda_kernel.cu:109-118,537-556 with the correct
+ *     tanh-gate derivative (the reference's unrolled kernel uses d_sigmoid there, cu:519-521).
+ */
+#ifndef FASTGRNN_B200_H_
+#define FASTGRNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGRNN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FGRNN_API __attribute__((visibility("default")))
+#else
+#define FGRNN_API
+#endif
+
+/* return codes */
+enum {
+  FGRNN_OK = 0,
+  FGRNN_ERR_NULL = 1,        /* a required pointer is NULL */
+  FGRNN_ERR_SHAPE = 2,       /* a dimension is out of the supported range */
+  FGRNN_ERR_ENUM = 3,        /* unknown nonlinearity / layout / dtype */
+  FGRNN_ERR_ALIGN = 4,       /* pointer or stride alignment requirement violated */
+  FGRNN_ERR_WORKSPACE = 5,   /* workspace missing or too small */
+  FGRNN_ERR_CUDA = 6,        /* a CUDA runtime call or kernel launch failed */
+  FGRNN_ERR_DEVICE = 7,      /* device is not an sm_100 part */
+  FGRNN_ERR_VERSION = 8      /* desc.abi_version mismatch */
+};
+
+/* nonlinearities: 0..2 as rnn.py:478 / rnn.py:751, 3..5 rnn.py:53-60 */
+enum {
+  FGRNN_NL_SIGMOID = 0,
+  FGRNN_NL_RELU = 1,
+  FGRNN_NL_TANH = 2,
+  FGRNN_NL_QUANT_TANH = 3,
+  FGRNN_NL_QUANT_SIGM = 4,
+  FGRNN_NL_QUANT_SIGM4 = 5
+};
+
+enum { FGRNN_LAYOUT_IH = 0, FGRNN_LAYOUT_HI = 1 };
+enum { FGRNN_F32 = 0, FGRNN_BF16 = 1 };
+
+/* kernel families (fgrnn_*_plan reports which one a descriptor selects) */
+enum {
+  FGRNN_PATH_GENERIC = 0,    /* any shape: weights streamed through L1/L2 */
+  FGRNN_PATH_SMEM = 1,       /* persistent FFMA kernel, weights resident in shared memory */
+  FGRNN_PATH_TCGEN05 = 2     /* tcgen05/TMEM kernel */
+};
+
+/* Problem description shared by forward and backward. */
+typedef struct FgrnnProblem {
+  int32_t abi_version;       /* FGRNN_ABI_VERSION */
+  int32_t device;            /* CUDA device ordinal the pointers live on */
+  int32_t B, T, I, H;        /* batch, steps, input features, hidden units */
+  int32_t rW, rU;            /* low-rank ranks, 0 = full rank */
+  int32_t gate_nl;           /* FGRNN_NL_* for z  (rnn.py:290) */
+  int32_t update_nl;         /* FGRNN_NL_* for c  (rnn.py:292); the reference CUDA path fixes tanh (cu:57) */
+  int32_t weight_layout;     /* FGRNN_LAYOUT_* */
+  int32_t x_dtype;           /* FGRNN_F32 | FGRNN_BF16 */
+  int32_t force_path;        /* -1 = auto, else FGRNN_PATH_* (tests / benchmarks) */
+  int32_t reserved0;
+  /* parameters (device pointers; the unused rank variant may be NULL) */
+  const float* W;  const float* U;
+  const float* W1; const float* W2;
+  const float* U1; const float* U2;
+  const float* bias_gate;    /* [1,H] */
+  const float* bias_update;  /* [1,H] */
+  const float* zeta;         /* [1,1] raw (pre-sigmoid) */
+  const float* nu;           /* [1,1] raw (pre-sigmoid) */
+  /* input sequence */
+  const void* x;  int64_t x_stride_b, x_stride_t;          /* [B,T,I] by strides */
+  const float* h0;           /* [B,H] contiguous, NULL = zeros (rnn.py:588-591, rnn.py:816-818) */
+} FgrnnProblem;
+
+/* forward (replaces forward / forward_unroll, cuda/fastgrnn_cuda.cpp:73,147) */
+typedef struct FgrnnForward {
+  FgrnnProblem p;
+  float* out;  int64_t out_stride_b, out_stride_t;         /* all T hidden states; may be NULL if h_last is set */
+  float* h_last;             /* optional [B,H]: h_T, for chunked streaming / last-state-only callers */
+  float* save_z;             /* optional [T,B,H] contiguous: z_s       (cu:340, returned by forward_unroll) */
+  float* save_c;             /* optional [T,B,H] contiguous: h_prime_s (cu:341) */
+  void* workspace; size_t workspace_bytes;
+} FgrnnForward;
+
+/* backward (replaces backward / backward_unroll, cuda/fastgrnn_cuda.cpp:109,182) */
+typedef struct FgrnnBackward {
+  FgrnnProblem p;
+  const float* grad_h; int64_t grad_stride_b, grad_stride_t;   /* dL/dh_t, all T */
+  const float* hs;     int64_t hs_stride_b, hs_stride_t;       /* hidden states from forward */
+  const float* z_s;          /* [T,B,H] contiguous, saved by forward (required) */
+  const float* c_s;          /* [T,B,H] contiguous, saved by forward (required) */
+  /* outputs; every pointer is optional except where noted. Parameter grads are OVERWRITTEN
+     (not accumulated), in p.weight_layout, shapes as the parameters. */
+  float* d_x;  int64_t dx_stride_b, dx_stride_t;           /* fp32, NULL = skip (layer-0 input) */
+  float* d_W;  float* d_U;  float* d_W1; float* d_W2; float* d_U1; float* d_U2;
+  float* d_bias_gate; float* d_bias_update;                /* [1,H] */
+  float* d_zeta; float* d_nu;                              /* [1,1] */
+  float* d_h0;                                             /* [B,H] */
+  void* workspace; size_t workspace_bytes;
+} FgrnnBackward;
+
+/* Bytes of device workspace the call needs (0 is possible). 256-byte aligned base required. */
+FGRNN_API size_t fgrnn_forward_workspace_bytes(const FgrnnForward* d);
+FGRNN_API size_t fgrnn_backward_workspace_bytes(const FgrnnBackward* d);
+
+/* Which kernel family the descriptor selects (FGRNN_PATH_*), or -1 on an invalid descriptor. */
+FGRNN_API int fgrnn_forward_plan(const FgrnnForward* d);
+FGRNN_API int fgrnn_backward_plan(const FgrnnBackward* d);
+
+/* Enqueue the work on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+   Asynchronous: returns after the launches are queued. Returns FGRNN_OK or an error code. */
+FGRNN_API int fgrnn_forward(const FgrnnForward* d, void* stream);
+FGRNN_API int fgrnn_backward(const FgrnnBackward* d, void* stream);
+
+/* Flat-bucket helper for data-parallel training: sums nothing, moves nothing across GPUs;
+   it only reports how the parameter gradients are laid out when the caller points the d_*
+   outputs into ONE contiguous fp32 bucket (so a single ncclAllReduce covers them).
+   Writes element offsets in the fixed order {W|W1,W2, U|U1,U2, bias_gate, bias_update, zeta, nu}
+   into offsets[8] (unused slots = -1) and returns the bucket length in floats. */
+FGRNN_API int64_t fgrnn_grad_bucket_layout(const FgrnnProblem* p, int64_t offsets[8]);
+
+FGRNN_API const char* fgrnn_strerror(int code);
+/* Thread-local detail of the last non-OK return on this thread ("" if none). */
+FGRNN_API const char* fgrnn_last_error_detail(void);
+FGRNN_API int fgrnn_abi_version(void);
+/* Cumulative number of kernels this library has launched in this process. */
+FGRNN_API uint64_t fgrnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTGRNN_B200_H_ */

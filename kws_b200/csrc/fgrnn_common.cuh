@@ -1,0 +1,121 @@
+// Shared device helpers and host-side plumbing for the FastGRNN engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "fastgrnn_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "kws_b200 kernels are written for sm_100a only"
+#endif
+
+namespace fgrnn {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error_detail(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define FGRNN_CUDA_TRY(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::fgrnn::set_error_detail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                                __FILE__, __LINE__);                                      \
+      return FGRNN_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+#define FGRNN_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ::fgrnn::set_error_detail("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+      return FGRNN_ERR_CUDA;                                                              \
+    }                                                                                     \
+    ::fgrnn::count_launch();                                                              \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller-provided workspace (sizes computed identically by the
+// *_workspace_bytes queries, which run it with base == nullptr).
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* b) : base(static_cast<char*>(b)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+  size_t total() const { return align_up(off, 256); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// nonlinearities (rnn.py:40-67) and their derivatives expressed on the OUTPUT value
+// (cuda/fastgrnn_cuda_kernel.cu:27-40 for sigmoid/relu/tanh; clamps: slope inside the window)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+template <int NL>
+__device__ __forceinline__ float act(float a) {
+  if (NL == FGRNN_NL_SIGMOID) return sigmoid_f(a);
+  if (NL == FGRNN_NL_TANH) return tanhf(a);
+  if (NL == FGRNN_NL_RELU) return fmaxf(a, 0.0f);
+  if (NL == FGRNN_NL_QUANT_TANH) return fmaxf(fminf(a, 1.0f), -1.0f);
+  if (NL == FGRNN_NL_QUANT_SIGM) return fmaxf(fminf((a + 1.0f) / 2.0f, 1.0f), 0.0f);
+  if (NL == FGRNN_NL_QUANT_SIGM4) return fmaxf(fminf((a + 2.0f) / 4.0f, 1.0f), 0.0f);
+  return a;
+}
+
+__device__ __forceinline__ float act_rt(int nl, float a) {
+  switch (nl) {
+    case FGRNN_NL_SIGMOID: return act<FGRNN_NL_SIGMOID>(a);
+    case FGRNN_NL_TANH: return act<FGRNN_NL_TANH>(a);
+    case FGRNN_NL_RELU: return act<FGRNN_NL_RELU>(a);
+    case FGRNN_NL_QUANT_TANH: return act<FGRNN_NL_QUANT_TANH>(a);
+    case FGRNN_NL_QUANT_SIGM: return act<FGRNN_NL_QUANT_SIGM>(a);
+    default: return act<FGRNN_NL_QUANT_SIGM4>(a);
+  }
+}
+
+// derivative d act / d a as a function of y = act(a)
+__device__ __forceinline__ float dact_rt(int nl, float y) {
+  switch (nl) {
+    case FGRNN_NL_SIGMOID: return y * (1.0f - y);
+    case FGRNN_NL_TANH: return 1.0f - y * y;
+    case FGRNN_NL_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    case FGRNN_NL_QUANT_TANH: return (y > -1.0f && y < 1.0f) ? 1.0f : 0.0f;
+    case FGRNN_NL_QUANT_SIGM: return (y > 0.0f && y < 1.0f) ? 0.5f : 0.0f;
+    default: return (y > 0.0f && y < 1.0f) ? 0.25f : 0.0f;
+  }
+}
+
+__device__ __forceinline__ float load_x(const void* x, int64_t idx, int dtype) {
+  if (dtype == FGRNN_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx]);
+  return reinterpret_cast<const float*>(x)[idx];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical problem view used by every kernel family.  "Canonical" weights are row-major
+// [K][N] in the oracle orientation (pre = A . Wc), independent of FgrnnProblem.weight_layout.
+// ---------------------------------------------------------------------------------------------
+struct Dims {
+  int B, T, I, H, rW, rU;
+  int gate_nl, update_nl, x_dtype;
+};
+
+}  // namespace fgrnn

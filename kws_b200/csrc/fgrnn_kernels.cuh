@@ -1,0 +1,82 @@
+// Kernel-family argument blocks and host launchers (internal to libfastgrnn_b200.so).
+#pragma once
+#include "fgrnn_common.cuh"
+
+namespace fgrnn {
+
+// ---- forward -----------------------------------------------------------------------------
+struct FwdArgs {
+  Dims d;
+  // canonical weights, row-major [K][N]:  Wc[I][H] | W1c[I][rW], W2c[rW][H];  Uc[H][H] | U1c[H][rU], U2c[rU][H]
+  const float *Wc, *Uc, *W1c, *W2c, *U1c, *U2c;
+  const float *bias_gate, *bias_update, *zeta, *nu;
+  const void* x; int64_t xsb, xst;
+  const float* h0;
+  float* out; int64_t osb, ost;
+  float* h_last; float* save_z; float* save_c;
+};
+
+int launch_gen_fwd(const FwdArgs& a, cudaStream_t stream);
+
+// ---- backward, serial part ---------------------------------------------------------------
+struct BwdRecArgs {
+  Dims d;
+  const float *zeta, *nu;
+  // transposed canonical recurrent weights: UT[n][k] = Uc[k][n];  U2T[H][rU];  U1T[rU][H]
+  const float *UT, *U2T, *U1T;
+  const float* grad_h; int64_t gsb, gst;
+  const float* hs; int64_t hsb, hst;
+  const float* h0;
+  const float *z_s, *c_s;
+  float* dpre_ws;       // [T][B][H]
+  float* rec_partial;   // [nCTA][2H+2]: d_bias_gate | d_bias_update | d_zeta(raw) | d_nu(raw)
+  float* d_h0;
+};
+
+int gen_bwd_rec_ctas(const Dims& d);
+int launch_gen_bwd_rec(const BwdRecArgs& a, cudaStream_t stream);
+
+// ---- backward, T-parallel contractions ---------------------------------------------------
+struct TnArgs {
+  int M, B, T, K, N;
+  const void* a; int64_t asb, ast; int a_dtype;
+  int a_shift;            // 1: row (t,b) reads a[t-1,b] and h0[b] at t == 0  (the h_{t-1} operand)
+  const float* a_h0;
+  const float* dpre;      // [M][N], m = t*B + b
+  float* partial;         // [nchunk][K][N]
+  int rows_per_chunk;
+};
+int launch_gemm_tn_partial(const TnArgs& a, int nchunk, cudaStream_t stream);
+
+struct NtArgs {
+  int M, B, N, I;
+  const float* dpre;      // [M][N]
+  const float* Wf;        // canonical [I][N]
+  float* dx; int64_t dsb, dst;
+};
+int launch_gemm_nt(const NtArgs& a, cudaStream_t stream);
+
+struct PrepJob { const float* src; float* dst; int rows, cols, transpose; };
+struct PrepJobs { int n; PrepJob job[8]; };
+int launch_prep(const PrepJobs& jobs, cudaStream_t stream);
+
+struct SmallGemm {
+  const float* A; int lda, transA;
+  const float* B; int ldb, transB;
+  float* C; int transC;
+  int M, N, K;
+};
+int launch_small_gemm(const SmallGemm& g, cudaStream_t stream);
+
+struct ReduceArgs {
+  int I, H, nchunk, nrec;
+  const float *partW, *partU;
+  float *dWc, *dUc;                 // destination (canonical or the caller's d_W/d_U)
+  int dW_transpose, dU_transpose;   // write destination transposed (HI layout, full rank)
+  const float* rec_partial;
+  float *d_bias_gate, *d_bias_update, *d_zeta, *d_nu;
+  const float *zeta, *nu;
+};
+int launch_reduce(const ReduceArgs& a, cudaStream_t stream);
+
+}  // namespace fgrnn
