@@ -195,7 +195,7 @@ def test_error_behaviour_matches_reference_wording():
         ext.forward_unroll(x, torch.randn(I, H, device=dev()).t(), cu["U"], cu["bg"], cu["bu"], cu["z"], cu["n"], h0, 0, e, e, e, e)
     with pytest.raises(RuntimeError, match="initial_h must be a CUDA tensor"):
         ext.forward_unroll(x, cu["W"], cu["U"], cu["bg"], cu["bu"], cu["z"], cu["n"], h0.cpu(), 0, e, e, e, e)
-    with pytest.raises(RuntimeError, match="unknown enum|nonlinearity"):
+    with pytest.raises((RuntimeError, ValueError), match="unknown enum|nonlinearity"):
         ext.forward_unroll(x, cu["W"], cu["U"], cu["bg"], cu["bu"], cu["z"], cu["n"], h0, 7, e, e, e, e)
     m = rnn.FastGRNN(I, H)      # parameters left on the CPU: no silent fallback
     with pytest.raises(RuntimeError, match="no CPU fallback"):
