@@ -89,17 +89,30 @@ struct FwdPlan {
   size_t ws_bytes;
 };
 
-int select_fwd_path(const FgrnnProblem& p) {
-  if (p.force_path >= 0) return p.force_path;
-  return FGRNN_PATH_GENERIC;
+bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+bool mult4(int64_t v) { return (v & 3) == 0; }
+
+// the persistent shared-memory family needs 16-byte vector access on every streamed tensor
+bool smem_fwd_ok(const FgrnnForward& f) {
+  const FgrnnProblem& p = f.p;
+  if (!smem_path_supports(dims_of(p))) return false;
+  const bool xok = p.x_dtype == FGRNN_BF16 ? (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 : aligned16(p.x);
+  return xok && mult4(p.x_stride_b) && mult4(p.x_stride_t) && aligned16(p.W) && aligned16(p.U) &&
+         aligned16(p.h0) && aligned16(f.out) && mult4(f.out_stride_b) && mult4(f.out_stride_t) &&
+         aligned16(f.h_last) && aligned16(f.save_z) && aligned16(f.save_c) && (!f.save_z == !f.save_c);
+}
+
+int select_fwd_path(const FgrnnForward& f) {
+  if (f.p.force_path >= 0) return f.p.force_path;
+  return smem_fwd_ok(f) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
 }
 
 FwdPlan plan_forward(const FgrnnForward& f, void* ws) {
   const FgrnnProblem& p = f.p;
   FwdPlan pl{};
-  pl.path = select_fwd_path(p);
+  pl.path = select_fwd_path(f);
   Carver cv(ws);
-  if (p.weight_layout == FGRNN_LAYOUT_HI) {
+  if (p.weight_layout == FGRNN_LAYOUT_HI && pl.path == FGRNN_PATH_GENERIC) {
     if (p.rW == 0) pl.Wc = cv.take<float>((size_t)p.I * p.H);
     else { pl.W1c = cv.take<float>((size_t)p.I * p.rW); pl.W2c = cv.take<float>((size_t)p.rW * p.H); }
     if (p.rU == 0) pl.Uc = cv.take<float>((size_t)p.H * p.H);
@@ -113,8 +126,11 @@ int validate_forward(const FgrnnForward& f) {
   int rc = validate_problem(f.p);
   if (rc) return rc;
   if (!f.out && !f.h_last && (int64_t)f.p.B * f.p.T > 0) return fail(FGRNN_ERR_NULL, "out and h_last are both NULL");
-  if (select_fwd_path(f.p) != FGRNN_PATH_GENERIC)
-    return fail(FGRNN_ERR_SHAPE, "forward path %d not available for this shape", select_fwd_path(f.p));
+  const int path = select_fwd_path(f);
+  if (path == FGRNN_PATH_SMEM && !smem_fwd_ok(f))
+    return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
+  if (path == FGRNN_PATH_TCGEN05)
+    return fail(FGRNN_ERR_SHAPE, "forward path %d not available for this shape", path);
   return FGRNN_OK;
 }
 
@@ -123,7 +139,7 @@ int validate_forward(const FgrnnForward& f) {
 // ----------------------------------------------------------------------------------------
 struct BwdPlan {
   int path;
-  int nchunk, rows_per_chunk, nrec;
+  int nchunk, rows_per_chunk, nrec, rows_per_cta;
   bool want_w, want_u;
   float *UT, *U2T, *U1T;      // workspace copies (nullptr => use caller's pointer directly)
   float *Wf;                  // canonical [I][H] for d_x (nullptr => caller's W usable directly)
@@ -131,26 +147,35 @@ struct BwdPlan {
   size_t ws_bytes;
 };
 
-int select_bwd_path(const FgrnnProblem& p) {
-  if (p.force_path >= 0) return p.force_path;
-  return FGRNN_PATH_GENERIC;
+bool smem_bwd_ok(const FgrnnBackward& g) {
+  const FgrnnProblem& p = g.p;
+  if (!smem_path_supports(dims_of(p))) return false;
+  return aligned16(p.U) && aligned16(p.h0) && aligned16(g.grad_h) && mult4(g.grad_stride_b) && mult4(g.grad_stride_t) &&
+         aligned16(g.hs) && mult4(g.hs_stride_b) && mult4(g.hs_stride_t) && aligned16(g.z_s) && aligned16(g.c_s) &&
+         aligned16(g.d_h0);
+}
+
+int select_bwd_path(const FgrnnBackward& g) {
+  if (g.p.force_path >= 0) return g.p.force_path;
+  return smem_bwd_ok(g) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
 }
 
 BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   const FgrnnProblem& p = g.p;
   BwdPlan pl{};
-  pl.path = select_bwd_path(p);
+  pl.path = select_bwd_path(g);
   const int64_t M = (int64_t)p.B * p.T;
   pl.nchunk = (int)std::min<int64_t>(128, std::max<int64_t>(1, M / 512));
   pl.rows_per_chunk = (int)((M + pl.nchunk - 1) / std::max(1, pl.nchunk));
   pl.rows_per_chunk = (pl.rows_per_chunk + 15) / 16 * 16;
   if (pl.rows_per_chunk < 16) pl.rows_per_chunk = 16;
-  pl.nrec = gen_bwd_rec_ctas(dims_of(p));
+  pl.rows_per_cta = pl.path == FGRNN_PATH_SMEM ? smem_rows_per_cta(dims_of(p), 148) : 0;
+  pl.nrec = pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p), pl.rows_per_cta) : gen_bwd_rec_ctas(dims_of(p));
   pl.want_w = g.d_W || g.d_W1 || g.d_W2;
   pl.want_u = g.d_U || g.d_U1 || g.d_U2;
   Carver cv(ws);
   const bool ih = p.weight_layout == FGRNN_LAYOUT_IH;
-  if (ih) {
+  if (ih && pl.path == FGRNN_PATH_GENERIC) {
     if (p.rU == 0) pl.UT = cv.take<float>((size_t)p.H * p.H);
     else { pl.U2T = cv.take<float>((size_t)p.H * p.rU); pl.U1T = cv.take<float>((size_t)p.rU * p.H); }
   }
@@ -173,8 +198,11 @@ int validate_backward(const FgrnnBackward& g) {
     if (!g.hs && g.p.T > 1) return fail(FGRNN_ERR_NULL, "hidden_states must be a CUDA tensor (NULL)");
     if (!g.z_s || !g.c_s) return fail(FGRNN_ERR_NULL, "z / h_prime must be CUDA tensors (NULL)");
   }
-  if (select_bwd_path(g.p) != FGRNN_PATH_GENERIC)
-    return fail(FGRNN_ERR_SHAPE, "backward path %d not available for this shape", select_bwd_path(g.p));
+  const int path = select_bwd_path(g);
+  if (path == FGRNN_PATH_SMEM && !smem_bwd_ok(g))
+    return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
+  if (path == FGRNN_PATH_TCGEN05)
+    return fail(FGRNN_ERR_SHAPE, "backward path %d not available for this shape", path);
   return FGRNN_OK;
 }
 
@@ -230,12 +258,12 @@ size_t fgrnn_backward_workspace_bytes(const FgrnnBackward* g) {
 
 int fgrnn_forward_plan(const FgrnnForward* f) {
   if (!f || validate_forward(*f)) return -1;
-  return select_fwd_path(f->p);
+  return select_fwd_path(*f);
 }
 
 int fgrnn_backward_plan(const FgrnnBackward* g) {
   if (!g || validate_backward(*g)) return -1;
-  return select_bwd_path(g->p);
+  return select_bwd_path(*g);
 }
 
 int64_t fgrnn_grad_bucket_layout(const FgrnnProblem* p, int64_t offsets[8]) {
@@ -273,6 +301,16 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     if (!f->workspace || f->workspace_bytes < pl.ws_bytes)
       return fail(FGRNN_ERR_WORKSPACE, "forward needs %zu workspace bytes, got %zu", pl.ws_bytes, f->workspace_bytes);
     if (reinterpret_cast<uintptr_t>(f->workspace) % 256) return fail(FGRNN_ERR_ALIGN, "workspace must be 256-byte aligned");
+  }
+
+  if (pl.path == FGRNN_PATH_SMEM) {
+    SmemFwdArgs s{};
+    s.d = dims_of(p); s.layout = p.weight_layout; s.W = p.W; s.U = p.U;
+    s.bias_gate = p.bias_gate; s.bias_update = p.bias_update; s.zeta = p.zeta; s.nu = p.nu;
+    s.x = p.x; s.xsb = p.x_stride_b; s.xst = p.x_stride_t; s.h0 = p.h0;
+    s.out = f->out; s.osb = f->out_stride_b; s.ost = f->out_stride_t;
+    s.h_last = f->h_last; s.save_z = f->save_z; s.save_c = f->save_c;
+    return launch_smem_fwd(s, smem_rows_per_cta(s.d, 148), stream);
   }
 
   FwdArgs a{};
@@ -346,7 +384,9 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
     jobs.job[jobs.n++] = PrepJob{src, dst, rows, cols, tr};
   };
   const float *UT = nullptr, *U2T = nullptr, *U1T = nullptr, *Wf = nullptr;
-  if (ih) {
+  if (pl.path == FGRNN_PATH_SMEM) {
+    // the persistent kernel transposes U on its way into shared memory
+  } else if (ih) {
     if (p.rU == 0) { add(p.U, pl.UT, p.H, p.H, 1); UT = pl.UT; }
     else { add(p.U2, pl.U2T, p.rU, p.H, 1); add(p.U1, pl.U1T, p.H, p.rU, 1); U2T = pl.U2T; U1T = pl.U1T; }
   } else {
@@ -371,6 +411,15 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   }
 
   // 2. serial reverse recurrence
+  if (pl.path == FGRNN_PATH_SMEM) {
+    SmemBwdArgs s{};
+    s.d = dims_of(p); s.layout = p.weight_layout; s.U = p.U; s.zeta = p.zeta; s.nu = p.nu;
+    s.grad_h = g->grad_h; s.gsb = g->grad_stride_b; s.gst = g->grad_stride_t;
+    s.hs = g->hs; s.hsb = g->hs_stride_b; s.hst = g->hs_stride_t;
+    s.h0 = p.h0; s.z_s = g->z_s; s.c_s = g->c_s;
+    s.dpre_ws = pl.dpre; s.rec_partial = pl.rec_partial; s.d_h0 = g->d_h0;
+    if ((rc = launch_smem_bwd_rec(s, pl.rows_per_cta, stream))) return rc;
+  } else {
   BwdRecArgs r{};
   r.d = dims_of(p);
   r.zeta = p.zeta; r.nu = p.nu;
@@ -380,6 +429,7 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   r.h0 = p.h0; r.z_s = g->z_s; r.c_s = g->c_s;
   r.dpre_ws = pl.dpre; r.rec_partial = pl.rec_partial; r.d_h0 = g->d_h0;
   if ((rc = launch_gen_bwd_rec(r, stream))) return rc;
+  }
 
   // 3. T-parallel outer-product sums as per-chunk partials (no atomics)
   if (pl.want_w) {

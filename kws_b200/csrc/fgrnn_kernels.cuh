@@ -79,4 +79,34 @@ struct ReduceArgs {
 };
 int launch_reduce(const ReduceArgs& a, cudaStream_t stream);
 
+// ---- persistent shared-memory family (fgrnn_smem.cu) ---------------------------------------
+struct SmemFwdArgs {
+  Dims d;
+  int layout;                       // FGRNN_LAYOUT_*: weights are read in the caller's layout
+  const float *W, *U;
+  const float *bias_gate, *bias_update, *zeta, *nu;
+  const void* x; int64_t xsb, xst;
+  const float* h0;
+  float* out; int64_t osb, ost;
+  float* h_last; float* save_z; float* save_c;
+};
+struct SmemBwdArgs {
+  Dims d;
+  int layout;
+  const float* U;
+  const float *zeta, *nu;
+  const float* grad_h; int64_t gsb, gst;
+  const float* hs; int64_t hsb, hst;
+  const float* h0;
+  const float *z_s, *c_s;
+  float* dpre_ws;
+  float* rec_partial;
+  float* d_h0;
+};
+bool smem_path_supports(const Dims& d);
+int smem_rows_per_cta(const Dims& d, int num_sms);
+int launch_smem_fwd(const SmemFwdArgs& a, int rows_per_cta, cudaStream_t stream);
+int smem_bwd_rec_ctas(const Dims& d, int rows_per_cta);
+int launch_smem_bwd_rec(const SmemBwdArgs& a, int rows_per_cta, cudaStream_t stream);
+
 }  // namespace fgrnn

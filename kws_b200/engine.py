@@ -191,7 +191,8 @@ def forward_plan(x, params, h0=None, *, layout="HI", batch_first=False, gate_nl=
     pr = _Problem(x, params, h0, layout, batch_first, gate_nl, update_nl, force_path)
     d = _lib.FgrnnForward()
     pr.fill(d.p)
-    d.out = 1  # non-NULL marker; nothing is launched
+    d.out = 0x10000  # aligned non-NULL marker; nothing is launched
+    d.out_stride_b, d.out_stride_t = (pr.T * pr.H, pr.H) if pr.batch_first else (pr.H, pr.B * pr.H)
     return _lib.PATH_NAMES.get(lib.fgrnn_forward_plan(C.byref(d)), "invalid")
 
 

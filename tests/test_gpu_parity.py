@@ -300,3 +300,48 @@ def test_empty_batch_and_sequence():
     with torch.no_grad():
         assert m(torch.zeros(0, 4, 8, device=dev())).shape == (0, 4, 16)
         assert m(torch.zeros(5, 0, 8, device=dev())).shape == (5, 0, 16)
+
+
+@pytest.mark.parametrize("path", ["generic", "smem"])
+@pytest.mark.parametrize("layout", ["IH", "HI"])
+@pytest.mark.parametrize("rows", ["32", "64"])
+def test_kernel_families_agree_with_oracle(path, layout, rows, monkeypatch):
+    """Every kernel family that covers the flagship shape (I=32, H=128, full rank) is checked on
+    its own, in both weight layouts, forward and backward, with a ragged batch."""
+    from kws_b200 import _lib, engine
+    monkeypatch.setenv("FGRNN_SMEM_ROWS", rows)
+    if path == "generic" and rows == "64":
+        pytest.skip("row override only affects the shared-memory family")
+    torch.manual_seed(77)
+    B, T, I, H = 77, 9, 32, 128
+    p = O.init_params(I, H)
+    p.bias_gate.add_(0.2 * torch.randn(1, H)); p.zeta.add_(0.3); p.nu.add_(0.5)
+    x = torch.randn(B, T, I); h0 = 0.5 * torch.randn(B, H); go = torch.randn(B, T, H)
+    ref = O.unroll(x, p, h0.clone().unsqueeze(0), True)
+    gref = O.autograd_grads(x, p, h0, go, True)
+    tens = p.tensors() if layout == "IH" else O.to_cuda_layout(p)
+    params = {k: v.to(dev()).contiguous() for k, v in tens.items()}
+    force = {"generic": _lib.PATH_GENERIC, "smem": _lib.PATH_SMEM}[path]
+    xg, h0g = x.to(dev()), h0.to(dev())
+    assert engine.forward_plan(xg, params, h0g, layout=layout, batch_first=True, force_path=force) == path
+    out, z_s, c_s, last = engine.forward(xg, params, h0g, layout=layout, batch_first=True,
+                                         save_for_backward=True, want_last=True, force_path=force)
+    assert state_ratio(out, ref) <= 1.0
+    assert torch.equal(last, out[:, -1])
+    g = engine.backward(go.to(dev()), xg, out, z_s, c_s, params, h0g, layout=layout, batch_first=True, force_path=force)
+    for k in p.tensors():
+        r = gref[k].t() if (layout == "HI" and k in ("W", "U")) else gref[k]
+        assert grad_ratio(g[k], r) <= 1.0, k
+    assert grad_ratio(g["x"], gref["x"]) <= 1.0 and grad_ratio(g["h0"], gref["h0"]) <= 1.0
+    # last-state-only mode (no [T,B,H] write at all)
+    _, _, _, last2 = engine.forward(xg, params, h0g, layout=layout, batch_first=True, want_states=False, force_path=force)
+    assert torch.equal(last2, last)
+
+
+def test_auto_plan_selects_persistent_kernel_for_flagship_shape():
+    from kws_b200 import engine
+    p = {k: v.to(dev()) for k, v in O.init_params(32, 128).tensors().items()}
+    x = torch.zeros(64, 99, 32, device=dev())
+    assert engine.forward_plan(x, p, None, layout="IH", batch_first=True) in ("smem", "tcgen05")
+    p2 = {k: v.to(dev()) for k, v in O.init_params(30, 96).tensors().items()}
+    assert engine.forward_plan(torch.zeros(4, 5, 30, device=dev()), p2, None, layout="IH", batch_first=True) == "generic"
