@@ -169,8 +169,8 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   pl.rows_per_chunk = (int)((M + pl.nchunk - 1) / std::max(1, pl.nchunk));
   pl.rows_per_chunk = (pl.rows_per_chunk + 15) / 16 * 16;
   if (pl.rows_per_chunk < 16) pl.rows_per_chunk = 16;
-  pl.rows_per_cta = pl.path == FGRNN_PATH_SMEM ? smem_rows_per_cta(dims_of(p), 148) : 0;
-  pl.nrec = pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p), pl.rows_per_cta) : gen_bwd_rec_ctas(dims_of(p));
+  pl.rows_per_cta = pl.path == FGRNN_PATH_SMEM ? smem_rows_per_cta(dims_of(p), 1) : 0;
+  pl.nrec = pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p)) : gen_bwd_rec_ctas(dims_of(p));
   pl.want_w = g.d_W || g.d_W1 || g.d_W2;
   pl.want_u = g.d_U || g.d_U1 || g.d_U2;
   Carver cv(ws);
@@ -310,7 +310,7 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     s.x = p.x; s.xsb = p.x_stride_b; s.xst = p.x_stride_t; s.h0 = p.h0;
     s.out = f->out; s.osb = f->out_stride_b; s.ost = f->out_stride_t;
     s.h_last = f->h_last; s.save_z = f->save_z; s.save_c = f->save_c;
-    return launch_smem_fwd(s, smem_rows_per_cta(s.d, 148), stream);
+    return launch_smem_fwd(s, stream);
   }
 
   FwdArgs a{};
@@ -418,7 +418,7 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
     s.hs = g->hs; s.hsb = g->hs_stride_b; s.hst = g->hs_stride_t;
     s.h0 = p.h0; s.z_s = g->z_s; s.c_s = g->c_s;
     s.dpre_ws = pl.dpre; s.rec_partial = pl.rec_partial; s.d_h0 = g->d_h0;
-    if ((rc = launch_smem_bwd_rec(s, pl.rows_per_cta, stream))) return rc;
+    if ((rc = launch_smem_bwd_rec(s, stream))) return rc;
   } else {
   BwdRecArgs r{};
   r.d = dims_of(p);

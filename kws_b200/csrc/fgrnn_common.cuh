@@ -64,6 +64,24 @@ struct Carver {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_f(float a) { return 1.0f / (1.0f + expf(-a)); }
 
+// Fast variants for the persistent kernels' default (sigmoid gate, tanh update) epilogue:
+// MUFU.EX2 / MUFU.RCP based, <= ~2 ulp; tanh switches to an odd minimax polynomial (max rel
+// error 1.1e-7) below 0.55 where 1 - 2/(1+e^{2x}) would cancel.  Margins vs the oracle are
+// asserted by the GPU parity tests.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float a) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * a)); }
+__device__ __forceinline__ float tanh_fast(float b) {
+  const float e = ex2_approx(2.8853900817779268f * b);
+  const float big = fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
+  const float s = b * b;
+  float t = fmaf(s, 0.016458360478281975f, -0.05268390104174614f);
+  t = fmaf(t, s, 0.13320937752723694f);
+  t = fmaf(t, s, -0.33332955837249756f);
+  const float small = fmaf(t * s, b, b);
+  return fabsf(b) < 0.55f ? small : big;
+}
+
 template <int NL>
 __device__ __forceinline__ float act(float a) {
   if (NL == FGRNN_NL_SIGMOID) return sigmoid_f(a);

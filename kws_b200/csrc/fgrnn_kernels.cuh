@@ -83,6 +83,7 @@ int launch_reduce(const ReduceArgs& a, cudaStream_t stream);
 struct SmemFwdArgs {
   Dims d;
   int layout;                       // FGRNN_LAYOUT_*: weights are read in the caller's layout
+  int fast_nl;                      // bit0: MUFU-based sigmoid, bit1: MUFU/polynomial tanh (default both)
   const float *W, *U;
   const float *bias_gate, *bias_update, *zeta, *nu;
   const void* x; int64_t xsb, xst;
@@ -104,9 +105,9 @@ struct SmemBwdArgs {
   float* d_h0;
 };
 bool smem_path_supports(const Dims& d);
-int smem_rows_per_cta(const Dims& d, int num_sms);
-int launch_smem_fwd(const SmemFwdArgs& a, int rows_per_cta, cudaStream_t stream);
-int smem_bwd_rec_ctas(const Dims& d, int rows_per_cta);
-int launch_smem_bwd_rec(const SmemBwdArgs& a, int rows_per_cta, cudaStream_t stream);
+int smem_rows_per_cta(const Dims& d, int backward);
+int launch_smem_fwd(const SmemFwdArgs& a, cudaStream_t stream);
+int smem_bwd_rec_ctas(const Dims& d);
+int launch_smem_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 
 }  // namespace fgrnn

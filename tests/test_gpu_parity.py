@@ -304,14 +304,14 @@ def test_empty_batch_and_sequence():
 
 @pytest.mark.parametrize("path", ["generic", "smem"])
 @pytest.mark.parametrize("layout", ["IH", "HI"])
-@pytest.mark.parametrize("rows", ["32", "64"])
-def test_kernel_families_agree_with_oracle(path, layout, rows, monkeypatch):
+@pytest.mark.parametrize("cfg", ["A", "A7", "B", "C"])
+def test_kernel_families_agree_with_oracle(path, layout, cfg, monkeypatch):
     """Every kernel family that covers the flagship shape (I=32, H=128, full rank) is checked on
     its own, in both weight layouts, forward and backward, with a ragged batch."""
     from kws_b200 import _lib, engine
-    monkeypatch.setenv("FGRNN_SMEM_ROWS", rows)
-    if path == "generic" and rows == "64":
-        pytest.skip("row override only affects the shared-memory family")
+    monkeypatch.setenv("FGRNN_SMEM_CFG", cfg)
+    if path == "generic" and cfg != "A":
+        pytest.skip("tile override only affects the shared-memory family")
     torch.manual_seed(77)
     B, T, I, H = 77, 9, 32, 128
     p = O.init_params(I, H)
