@@ -102,6 +102,11 @@ bool smem_fwd_ok(const FgrnnForward& f) {
          aligned16(f.h_last) && aligned16(f.save_z) && aligned16(f.save_c) && (!f.save_z == !f.save_c);
 }
 
+// tcgen05 family: same streaming requirements, inference only (no z/c save buffers)
+bool tc_fwd_ok(const FgrnnForward& f) {
+  return smem_fwd_ok(f) && tc_path_supports(dims_of(f.p)) && !f.save_z && !f.save_c;
+}
+
 int select_fwd_path(const FgrnnForward& f) {
   if (f.p.force_path >= 0) return f.p.force_path;
   return smem_fwd_ok(f) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
@@ -129,8 +134,8 @@ int validate_forward(const FgrnnForward& f) {
   const int path = select_fwd_path(f);
   if (path == FGRNN_PATH_SMEM && !smem_fwd_ok(f))
     return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
-  if (path == FGRNN_PATH_TCGEN05)
-    return fail(FGRNN_ERR_SHAPE, "forward path %d not available for this shape", path);
+  if (path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f))
+    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, I in {16,32}, sigmoid/tanh, no save buffers, 16-byte aligned tensors");
   return FGRNN_OK;
 }
 
@@ -303,14 +308,14 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     if (reinterpret_cast<uintptr_t>(f->workspace) % 256) return fail(FGRNN_ERR_ALIGN, "workspace must be 256-byte aligned");
   }
 
-  if (pl.path == FGRNN_PATH_SMEM) {
+  if (pl.path == FGRNN_PATH_SMEM || pl.path == FGRNN_PATH_TCGEN05) {
     SmemFwdArgs s{};
     s.d = dims_of(p); s.layout = p.weight_layout; s.W = p.W; s.U = p.U;
     s.bias_gate = p.bias_gate; s.bias_update = p.bias_update; s.zeta = p.zeta; s.nu = p.nu;
     s.x = p.x; s.xsb = p.x_stride_b; s.xst = p.x_stride_t; s.h0 = p.h0;
     s.out = f->out; s.osb = f->out_stride_b; s.ost = f->out_stride_t;
     s.h_last = f->h_last; s.save_z = f->save_z; s.save_c = f->save_c;
-    return launch_smem_fwd(s, stream);
+    return pl.path == FGRNN_PATH_TCGEN05 ? launch_tc_fwd(s, stream) : launch_smem_fwd(s, stream);
   }
 
   FwdArgs a{};

@@ -110,4 +110,8 @@ int launch_smem_fwd(const SmemFwdArgs& a, cudaStream_t stream);
 int smem_bwd_rec_ctas(const Dims& d);
 int launch_smem_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 
+// ---- tcgen05 / TMEM family (fgrnn_tc.cu) ---------------------------------------------------
+bool tc_path_supports(const Dims& d);
+int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream);
+
 }  // namespace fgrnn
