@@ -102,9 +102,11 @@ bool smem_fwd_ok(const FgrnnForward& f) {
          aligned16(f.h_last) && aligned16(f.save_z) && aligned16(f.save_c) && (!f.save_z == !f.save_c);
 }
 
-// tcgen05 family: same streaming requirements, inference only (no z/c save buffers)
+// tcgen05 family: same streaming requirements; x is fetched by TMA (16-byte aligned base and strides)
 bool tc_fwd_ok(const FgrnnForward& f) {
-  return smem_fwd_ok(f) && tc_path_supports(dims_of(f.p)) && !f.save_z && !f.save_c;
+  const FgrnnProblem& p = f.p;
+  return smem_fwd_ok(f) && tc_path_supports(dims_of(p)) &&
+         tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T);
 }
 
 int select_fwd_path(const FgrnnForward& f) {
@@ -135,7 +137,7 @@ int validate_forward(const FgrnnForward& f) {
   if (path == FGRNN_PATH_SMEM && !smem_fwd_ok(f))
     return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
   if (path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f))
-    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, I in {16,32}, sigmoid/tanh, no save buffers, 16-byte aligned tensors");
+    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, I%%8==0, I<=64, sigmoid gate / tanh update, 16-byte aligned tensors and strides");
   return FGRNN_OK;
 }
 

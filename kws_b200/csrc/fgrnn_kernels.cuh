@@ -112,6 +112,7 @@ int launch_smem_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 
 // ---- tcgen05 / TMEM family (fgrnn_tc.cu) ---------------------------------------------------
 bool tc_path_supports(const Dims& d);
+bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, int T);
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream);
 
 }  // namespace fgrnn

@@ -1,5 +1,5 @@
-"""GPU: the tcgen05/TMEM forward recurrence (fp16 hi+lo split, 3 MMAs per product, fp32
-accumulation in TMEM) against the CPU oracle with the north-star tolerances."""
+"""GPU: the tcgen05/TMEM forward recurrence (weights in tensor memory, fp16 hi+lo split, three
+accumulators per sub-tile, x by TMA) against the CPU oracle with the north-star tolerances."""
 import pytest
 import torch
 
@@ -9,7 +9,7 @@ from oracle import fastgrnn_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _run(B, T, I, layout, h0_given, seed, x_bf16=False, wscale=1.0):
+def _run(B, T, I, layout, h0_given, seed, x_bf16=False, wscale=1.0, batch_first=True, save=False):
     from kws_b200 import _lib, engine
     torch.manual_seed(seed)
     p = O.init_params(I, 128)
@@ -23,33 +23,60 @@ def _run(B, T, I, layout, h0_given, seed, x_bf16=False, wscale=1.0):
     tens = p.tensors() if layout == "IH" else O.to_cuda_layout(p)
     params = {k: v.to(dev()).contiguous() for k, v in tens.items()}
     xg = x.to(dev())
+    if not batch_first:
+        xg = xg.transpose(0, 1).contiguous()
     if x_bf16:
         xg = xg.bfloat16()
     h0g = None if h0 is None else h0.to(dev())
-    assert engine.forward_plan(xg, params, h0g, layout=layout, batch_first=True, force_path=_lib.PATH_TCGEN05) == "tcgen05"
-    out, _, _, last = engine.forward(xg, params, h0g, layout=layout, batch_first=True, want_last=True,
-                                     force_path=_lib.PATH_TCGEN05)
+    assert engine.forward_plan(xg, params, h0g, layout=layout, batch_first=batch_first, force_path=_lib.PATH_TCGEN05) == "tcgen05"
+    out, z_s, c_s, last = engine.forward(xg, params, h0g, layout=layout, batch_first=batch_first, want_last=True,
+                                         save_for_backward=save, force_path=_lib.PATH_TCGEN05)
     torch.cuda.synchronize()
-    return out, last, ref
+    if not batch_first:
+        out = out.transpose(0, 1)
+    return out, last, ref, z_s, c_s
 
 
 @pytest.mark.parametrize("B,T,I,layout,h0", [
-    (128, 1, 32, "IH", False),
+    (64, 1, 32, "IH", False),
     (128, 3, 32, "IH", True),
-    (77, 9, 32, "HI", True),          # ragged single tile
-    (300, 17, 16, "IH", False),       # three tiles, I = 16
+    (77, 9, 32, "HI", True),          # ragged single CTA, second sub-tile partly empty
+    (300, 17, 16, "IH", False),       # five CTAs, I = 16
+    (40, 5, 64, "HI", True),          # I = 64 (MFCC + deltas, preprocessing.py)
+    (33, 4, 24, "IH", True),          # I = 24: K padded to 32 with zeros
     (64, 99, 32, "IH", False),        # BASELINE config-1 shape
 ])
 def test_tcgen05_forward_vs_oracle(B, T, I, layout, h0):
-    out, last, ref = _run(B, T, I, layout, h0, seed=11 + B + T)
+    out, last, ref, _, _ = _run(B, T, I, layout, h0, seed=11 + B + T)
     r = state_ratio(out, ref)
     assert r <= 1.0, r
     assert torch.equal(last, out[:, -1])
 
 
+def test_tcgen05_time_major_and_saved_gates():
+    out, last, ref, z_s, c_s = _run(70, 6, 32, "HI", True, seed=3, batch_first=False, save=True)
+    assert state_ratio(out, ref) <= 1.0
+    # z_s, c_s [T,B,H] reproduce the state update h_t = z h_{t-1} + (sz (1 - z) + sn) c   (rnn.py:294-295)
+    assert z_s.shape == (6, 70, 128) and c_s.shape == (6, 70, 128)
+    assert float(z_s.min()) >= 0.0 and float(z_s.max()) <= 1.0 and float(c_s.abs().max()) <= 1.0
+
+
 def test_tcgen05_bf16_input_and_weight_scales():
-    out, _, ref = _run(96, 20, 32, "IH", True, seed=5, x_bf16=True)
+    out, _, ref, _, _ = _run(96, 20, 32, "IH", True, seed=5, x_bf16=True)
     assert state_ratio(out, ref) <= 1.0
     for ws in (0.2, 3.0):             # power-of-two operand scaling adapts to the weight magnitude
-        out, _, ref = _run(40, 6, 32, "HI", False, seed=6, wscale=ws)
+        out, _, ref, _, _ = _run(40, 6, 32, "HI", False, seed=6, wscale=ws)
         assert state_ratio(out, ref) <= 1.0, ws
+
+
+def test_tcgen05_matches_ffma_path_on_a_full_wave():
+    """8192 rows (128 CTAs): the two kernel families agree to well inside the tolerance."""
+    from kws_b200 import _lib, engine
+    torch.manual_seed(0)
+    p = O.init_params(32, 128)
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    x = torch.randn(8192, 12, 32, device=dev())
+    a = engine.forward(x, params, None, layout="IH", batch_first=True, force_path=_lib.PATH_TCGEN05)[0]
+    b = engine.forward(x, params, None, layout="IH", batch_first=True, force_path=_lib.PATH_SMEM)[0]
+    torch.cuda.synchronize()
+    assert state_ratio(a, b.cpu()) <= 1.0
