@@ -166,18 +166,90 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
   return L;
 }
 
-// gate update for one element (rnn.py:289-295): tot = 2^S * pre
-struct EpiConst { float kS, k2S, cg, cu, sz, szn; };
+// split without the range clamp (|v*scale| < 65504 is guaranteed by the caller)
+__device__ __forceinline__ void split2_nc(float a, float b, float scale, uint32_t& hi, uint32_t& lo) {
+  a *= scale; b *= scale;
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// gate update for one element (rnn.py:289-295): tot = 2^S * pre.
+//   e_g = exp(-(pre + b_g)), e_u = exp(-2 (pre + b_u));  z = 1/(1+e_g);  c = (1-e_u)/(1+e_u);  one MUFU.RCP serves
+//   both:  r = 1/((1+e_g)(1+e_u)).  tot is clamped from below (per-unit constant tmin) so that both exponents
+//   stay <= 60 and the product stays finite; at the clamp z < 1e-18 and c = -1 to fp32 precision.
+struct EpiConst { float kS, k2S, cg, cu, sz, szn, tmin; };
 __device__ __forceinline__ float gate_update(float tot, float h, const EpiConst& k, float& z_out, float& c_out) {
-  const float yg = fminf(fmaf(tot, k.kS, k.cg), 60.0f);        // -(pre + b_g) * log2(e)
-  const float yu = fminf(fmaf(tot, k.k2S, k.cu), 60.0f);       // -2 (pre + b_u) * log2(e)
-  const float eg = ex2_approx(yg), eu = ex2_approx(yu);
+  tot = fmaxf(tot, k.tmin);
+  const float eg = ex2_approx(fmaf(tot, k.kS, k.cg));          // -(pre + b_g) * log2(e)
+  const float eu = ex2_approx(fmaf(tot, k.k2S, k.cu));         // -2 (pre + b_u) * log2(e)
   const float a = 1.0f + eg, b = 1.0f + eu;
   const float r = rcp_approx(a * b);
   const float z = r * b;                                       // sigmoid(pre + b_g)           rnn.py:290
   const float c = (1.0f - eu) * (r * a);                       // tanh(pre + b_u)              rnn.py:292
   z_out = z; c_out = c;
   return fmaf(z, h, fmaf(-k.sz, z, k.szn) * c);                // z h + (sz (1 - z) + sn) c    rnn.py:294-295
+}
+
+// Epilogue main loop of one warp.  Thread = hidden unit n; it owns rows [rh*16, rh*16+16) of both sub-tiles.
+struct EpiCtx {
+  uint32_t bar_dfull, bar_hready;     // shared addresses of the [NT] barrier arrays
+  uint32_t acc;                       // TMEM address: lane quadrant | TM_ACC + rh*16
+  unsigned char* hop;                 // operand-tile address of (sub-tile 0, row group rh*2, k = n), hi part
+  float* out;                         // &out[row0 + rh*16][t = 0][n]  (or null)
+  float* zs; float* cs;               // &save[t = 0][row0 + rh*16][n]
+  uint32_t out_row, out_step;         // element strides of `out`
+  uint32_t zc_step;                   // B*H
+  int rows_left;                      // B - (row0 + rh*16): rows >= rows_left (per sub-tile offset) are padding
+  int T;
+  float scale_h;
+};
+
+template <bool HAS_OUT, bool SAVE, bool MASKED>
+__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float (&hst)[TC_NT][16]) {
+  float* outp = cx.out; float* zp = cx.zs; float* cp = cx.cs;
+  for (int t = 0; t < cx.T; ++t) {
+#pragma unroll
+    for (int s = 0; s < TC_NT; ++s) {
+      mbar_wait(cx.bar_dfull + s * 8, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float vc[8], v1[8], v2[8];
+        const uint32_t acc = cx.acc + s * TM_ACC_PER_TILE + g * 8;
+        tmem_ld8(acc, vc);
+        tmem_ld8(acc + TC_NS, v1);
+        tmem_ld8(acc + 2 * TC_NS, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rj = s * TC_NS + g * 8 + j;                 // row offset from this thread's first row
+          const float tot = (vc[j] + v2[j]) + v1[j];
+          float z, c;
+          const float hn = gate_update(tot, hst[s][g * 8 + j], kc, z, c);
+          hst[s][g * 8 + j] = hn;
+          if (!MASKED || rj < cx.rows_left) {
+            if (HAS_OUT) outp[(uint32_t)rj * cx.out_row] = hn;
+            if (SAVE) { zp[rj * TC_H] = z; cp[rj * TC_H] = c; }
+          }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split2_nc(hst[s][g * 8 + 2 * q], hst[s][g * 8 + 2 * q + 1], cx.scale_h, hi[q], lo[q]);
+        unsigned char* p = cx.hop + s * (2 * TC_NS * TC_H * 2) + g * 128;
+        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();                        // st.shared of the h tile -> visible to tcgen05.mma
+      tc_fence_before();                               // tcgen05.ld of D done before the next MMAs overwrite it
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + s * 8);
+    }
+    if (HAS_OUT) outp += cx.out_step;
+    if (SAVE) { zp += cx.zc_step; cp += cx.zc_step; }
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
@@ -375,22 +447,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
       kc.kS = -LOG2E * unscale; kc.k2S = -2.0f * LOG2E * unscale;
       kc.cg = -LOG2E * __ldg(a.bias_gate + n); kc.cu = -2.0f * LOG2E * __ldg(a.bias_update + n);
       kc.sz = sz; kc.szn = sz + sn;
+      // tot >= tmin  <=>  both exponents <= 60
+      kc.tmin = fmaxf((60.0f - kc.cg) / kc.kS, (60.0f - kc.cu) / kc.k2S);
     }
 
     // state: this thread owns h[row][n] for 16 rows of each sub-tile
     float hst[TC_NT][16];
-    // operand-tile address of (sub-tile s, 8-row group g, k = n), hi part; lo part is +NS*128*2
-    auto hop_addr = [&](int s, int g) {
-      return sm + L.h_op + (s * 2) * TC_NS * TC_H * 2 + (n >> 3) * ((TC_NS >> 3) * 128) + g * 128 + (n & 7) * 16;
-    };
-    auto stash_h = [&](int s, int g, const float* hv) {       // 8 consecutive rows -> one 16-byte chunk each of hi and lo
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) split2(hv[2 * q], hv[2 * q + 1], scale_h, hi[q], lo[q]);
-      unsigned char* p = hop_addr(s, g);
-      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    };
+    unsigned char* hop = sm + L.h_op + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
 #pragma unroll
     for (int s = 0; s < TC_NT; ++s) {
 #pragma unroll
@@ -398,8 +461,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         const int row = row0 + s * TC_NS + rh * 16 + j;
         hst[s][j] = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
       }
-      stash_h(s, rh * 2, &hst[s][0]);
-      stash_h(s, rh * 2 + 1, &hst[s][8]);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split2(hst[s][g * 8 + 2 * q], hst[s][g * 8 + 2 * q + 1], scale_h, hi[q], lo[q]);
+        unsigned char* p = hop + s * (2 * TC_NS * TC_H * 2) + g * 128;
+        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -407,43 +477,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     __syncwarp();
     if (lane == 0) { mbar_arrive(bar(B_HREADY + 0)); mbar_arrive(bar(B_HREADY + 1)); }   // phase 0: h_{-1} ready
 
-    for (int t = 0; t < d.T; ++t) {
-      const bool last = t == d.T - 1;
+    EpiCtx cx;
+    cx.bar_dfull = bar(B_DFULL); cx.bar_hready = bar(B_HREADY);
+    cx.acc = tmem + lane_base + TM_ACC + rh * 16;
+    cx.hop = hop;
+    const int first_row = row0 + rh * 16;
+    cx.out = a.out ? a.out + (size_t)first_row * a.osb + n : nullptr;
+    cx.zs = a.save_z ? a.save_z + (size_t)first_row * TC_H + n : nullptr;
+    cx.cs = a.save_c ? a.save_c + (size_t)first_row * TC_H + n : nullptr;
+    cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
+    cx.rows_left = d.B - first_row; cx.T = d.T; cx.scale_h = scale_h;
+    const bool masked = row0 + TC_ROWS > d.B;
+    const int variant = (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
+    switch (variant) {
+      case 0: epilogue_loop<false, false, false>(cx, kc, hst); break;
+      case 1: epilogue_loop<false, false, true>(cx, kc, hst); break;
+      case 2: epilogue_loop<false, true, false>(cx, kc, hst); break;
+      case 3: epilogue_loop<false, true, true>(cx, kc, hst); break;
+      case 4: epilogue_loop<true, false, false>(cx, kc, hst); break;
+      case 5: epilogue_loop<true, false, true>(cx, kc, hst); break;
+      case 6: epilogue_loop<true, true, false>(cx, kc, hst); break;
+      default: epilogue_loop<true, true, true>(cx, kc, hst); break;
+    }
+    if (a.h_last) {
 #pragma unroll
-      for (int s = 0; s < TC_NT; ++s) {
-        mbar_wait(bar(B_DFULL + s), t & 1);
-        tc_fence_after();
-        const uint32_t accC = tmem + lane_base + TM_ACC + s * TM_ACC_PER_TILE + rh * 16;
+      for (int s = 0; s < TC_NT; ++s)
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float vc[8], v1[8], v2[8];
-          tmem_ld8(accC + g * 8, vc);
-          tmem_ld8(accC + TC_NS + g * 8, v1);
-          tmem_ld8(accC + 2 * TC_NS + g * 8, v2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float tot = (vc[j] + v2[j]) + v1[j];
-            float z, c;
-            const float hn = gate_update(tot, hst[s][g * 8 + j], kc, z, c);
-            hst[s][g * 8 + j] = hn;
-            const int row = row0 + s * TC_NS + rh * 16 + g * 8 + j;
-            if (row < d.B) {
-              if (a.out) a.out[(size_t)row * a.osb + (size_t)t * a.ost + n] = hn;
-              if (a.save_z) {
-                a.save_z[((size_t)t * d.B + row) * TC_H + n] = z;
-                a.save_c[((size_t)t * d.B + row) * TC_H + n] = c;
-              }
-              if (last && a.h_last) a.h_last[(size_t)row * TC_H + n] = hn;
-            }
-          }
-          stash_h(s, rh * 2 + g, &hst[s][g * 8]);
+        for (int j = 0; j < 16; ++j) {
+          const int row = first_row + s * TC_NS + j;
+          if (row < d.B) a.h_last[(size_t)row * TC_H + n] = hst[s][j];
         }
-        fence_proxy_async_smem();                      // st.shared of the h tile -> visible to tcgen05.mma
-        tc_fence_before();                             // tcgen05.ld of D done before the next MMAs overwrite it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_HREADY + s));
-      }
     }
   }
   tc_fence_before();
