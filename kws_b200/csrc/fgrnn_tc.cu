@@ -38,16 +38,34 @@ constexpr int TC_H = 128;                      // hidden size = UMMA M
 constexpr int TC_NS = 32;                      // batch rows per sub-tile = UMMA N
 constexpr int TC_NT = 2;                       // sub-tiles per CTA
 constexpr int TC_ROWS = TC_NS * TC_NT;         // 64 batch rows per CTA
-constexpr int TC_CONV_WARPS = 3;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 32 * (1 + TC_CONV_WARPS + TC_EPI_WARPS);   // 384
+constexpr int TC_CONV_WARPS = 4;                // each owns 16 rows of the x tile: own TMA box, own raw ring
+constexpr int TC_CONV_ROWS = 16;
+constexpr int TC_XBUF = 4;                      // x operand tile buffers (the converters run up to 3 steps ahead)
+constexpr int TC_EPI_WARPS = 16;                // 4 TMEM lane quadrants x 4 row groups (8 rows of EACH sub-tile)
+constexpr int TC_MMA_WARPS = 3;                 // the 30 MMAs of a sub-tile step are issued by three warps, 10 each
+constexpr int TC_THREADS = 32 * (TC_MMA_WARPS + TC_CONV_WARPS + TC_EPI_WARPS);   // 736
 constexpr int TC_RAW_STAGES = 4;
 constexpr int TC_MAX_KI = 64;                  // input features padded to a multiple of 16, <= 64
 // tensor-memory column map
 constexpr int TM_U_HI = 0, TM_U_LO = 64, TM_W_HI = 128, TM_W_LO = 160, TM_ACC = 192;
-constexpr int TM_ACC_PER_TILE = 3 * TC_NS;     // C | M1 | M2
+constexpr int TM_ACC_PER_TILE = 4 * TC_NS;     // CA | CB | M1 | M2
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_SH_EXP = 4;                   // h is scaled by 2^4 before the fp16 split
+
+// Developer trace (tools/tc_trace.cu defines FGRNN_TC_TRACE): clock64 stamps of CTA 0 for steps [16, 20)
+#ifdef FGRNN_TC_TRACE
+__device__ long long g_tc_trace[4 * 2 * 16];
+#define TC_TRACE(t, s, slot)                                                                         \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) >= 16 && (t) < 20)                         \
+      g_tc_trace[(((t) - 16) * 2 + (s)) * 16 + (slot)] = clock64();                                  \
+  } while (0)
+__device__ unsigned long long g_tc_cta_time[1024 * 4];
+__device__ __forceinline__ unsigned long long tc_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC_CTA_TIME(slot) do { if (threadIdx.x == 128 && blockIdx.x < 1024) g_tc_cta_time[blockIdx.x * 4 + (slot)] = tc_globaltimer(); } while (0)
+#else
+#define TC_TRACE(t, s, slot) do { } while (0)
+#define TC_CTA_TIME(slot) do { } while (0)
+#endif
 
 // ---- raw PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,12 +78,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Blocking wait: try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs
+// out, so waiting warps do not burn issue slots polling (an unhinted try_wait loop took 25 % of all issued
+// instructions away from the epilogue warps).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (spins > (1u << 26)) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (spins > (1u << 20)) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
   }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -100,6 +121,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "r"(taddr) : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -154,43 +184,63 @@ struct TcSmemLayout {
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
   TcSmemLayout L;
   L.x_tile_bytes = TC_NS * KI * 2;
-  L.raw_stage_bytes = TC_ROWS * I * esz;
+  L.raw_stage_bytes = TC_CONV_ROWS * I * esz;                   // per converter warp
   L.h_op = 0;                                                   // [NT][hi|lo][NS*128*2]
-  L.x_op = L.h_op + TC_NT * 2 * TC_NS * TC_H * 2;               // [2 buffers][NT][hi|lo][x_tile_bytes]
-  L.raw = L.x_op + 2 * TC_NT * 2 * L.x_tile_bytes;              // [RAW_STAGES][raw_stage_bytes], 128-byte aligned
+  L.x_op = L.h_op + TC_NT * 2 * TC_NS * TC_H * 2;               // [XBUF][NT][hi|lo][x_tile_bytes]
+  L.raw = L.x_op + TC_XBUF * TC_NT * 2 * L.x_tile_bytes;        // [CONV_WARPS][RAW_STAGES][raw_stage_bytes], 128-byte aligned
   L.raw = (L.raw + 127) & ~127;
-  L.bars = L.raw + TC_RAW_STAGES * L.raw_stage_bytes;
+  L.bars = L.raw + TC_CONV_WARPS * TC_RAW_STAGES * L.raw_stage_bytes;
   L.bars = (L.bars + 15) & ~15;
-  L.misc = L.bars + 24 * 8;
+  L.misc = L.bars + 32 * 8;
   L.total = L.misc + 256;
   return L;
 }
 
-// split without the range clamp (|v*scale| < 65504 is guaranteed by the caller)
-__device__ __forceinline__ void split2_nc(float a, float b, float scale, uint32_t& hi, uint32_t& lo) {
-  a *= scale; b *= scale;
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+// Gate update of two rows at once on the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2), rnn.py:289-295.
+//   tot = 2^S * pre.   e_g = exp(-(pre + b_g)),  e_u = exp(-2 (pre + b_u));   one MUFU.RCP serves both gates:
+//   r = 1/((1+e_g)(1+e_u));  z = r (1+e_u) = sigmoid(pre + b_g);  c = 2 r (1+e_g) - 1 = tanh(pre + b_u);
+//   h' = z (h - sz c) + (sz + sn) c   ( = z h + (sz (1 - z) + sn) c ).
+// tot is clamped from below (per-unit constant tmin) so that both exponents stay <= 60 and the product stays
+// finite; at the clamp z < 1e-18 and c = -1 to fp32 precision.
+struct EpiConst { float2 kS, k2S, cg, cu, msz, szn, tmin_; float tmin; };
+#ifndef FGRNN_TC_C_FORM
+#define FGRNN_TC_C_FORM 0       // 1: c = (1 - e_u) * (r a) instead of 2 r a - 1
+#endif
+#ifndef FGRNN_TC_ONE_EX2
+#define FGRNN_TC_ONE_EX2 1      // 1: e_u = e_g^2 * exp(2 (b_g - b_u)) saves one MUFU.EX2 per element
+#endif
+__device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiConst& k, float2& z, float2& c) {
+  tot.x = fmaxf(tot.x, k.tmin); tot.y = fmaxf(tot.y, k.tmin);
+  const float2 ag = __ffma2_rn(tot, k.kS, k.cg);               // -(pre + b_g) * log2(e)
+  float2 eg, eu;
+  eg.x = ex2_approx(ag.x); eg.y = ex2_approx(ag.y);
+#if FGRNN_TC_ONE_EX2
+  eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                   // cu = exp(2 (b_g - b_u))
+#else
+  const float2 au = __ffma2_rn(tot, k.k2S, k.cu);              // -2 (pre + b_u) * log2(e)
+  eu.x = ex2_approx(au.x); eu.y = ex2_approx(au.y);
+#endif
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 a = __fadd2_rn(eg, one), b = __fadd2_rn(eu, one);
+  const float2 ab = __fmul2_rn(a, b);
+  float2 r;
+  r.x = rcp_approx(ab.x); r.y = rcp_approx(ab.y);
+  z = __fmul2_rn(r, b);                                        // rnn.py:290
+#if FGRNN_TC_C_FORM
+  c = __fmul2_rn(__fadd2_rn(make_float2(-eu.x, -eu.y), one), __fmul2_rn(r, a));            // (1 - e_u) / (1 + e_u)
+#else
+  c = __ffma2_rn(__fmul2_rn(r, a), make_float2(2.0f, 2.0f), make_float2(-1.0f, -1.0f));   // rnn.py:292
+#endif
+  return __ffma2_rn(z, __ffma2_rn(k.msz, c, h), __fmul2_rn(k.szn, c));                      // rnn.py:294-295
 }
 
-// gate update for one element (rnn.py:289-295): tot = 2^S * pre.
-//   e_g = exp(-(pre + b_g)), e_u = exp(-2 (pre + b_u));  z = 1/(1+e_g);  c = (1-e_u)/(1+e_u);  one MUFU.RCP serves
-//   both:  r = 1/((1+e_g)(1+e_u)).  tot is clamped from below (per-unit constant tmin) so that both exponents
-//   stay <= 60 and the product stays finite; at the clamp z < 1e-18 and c = -1 to fp32 precision.
-struct EpiConst { float kS, k2S, cg, cu, sz, szn, tmin; };
-__device__ __forceinline__ float gate_update(float tot, float h, const EpiConst& k, float& z_out, float& c_out) {
-  tot = fmaxf(tot, k.tmin);
-  const float eg = ex2_approx(fmaf(tot, k.kS, k.cg));          // -(pre + b_g) * log2(e)
-  const float eu = ex2_approx(fmaf(tot, k.k2S, k.cu));         // -2 (pre + b_u) * log2(e)
-  const float a = 1.0f + eg, b = 1.0f + eu;
-  const float r = rcp_approx(a * b);
-  const float z = r * b;                                       // sigmoid(pre + b_g)           rnn.py:290
-  const float c = (1.0f - eu) * (r * a);                       // tanh(pre + b_u)              rnn.py:292
-  z_out = z; c_out = c;
-  return fmaf(z, h, fmaf(-k.sz, z, k.szn) * c);                // z h + (sz (1 - z) + sn) c    rnn.py:294-295
+// h (two rows) -> fp16 hi pair and fp16 lo pair (residual, exact subtraction); |h| < 65504
+__device__ __forceinline__ void split_pair(float2 h, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __float22half2_rn(h);
+  const float2 hf = __half22float2(hh);
+  const __half2 hl = __float22half2_rn(__fadd2_rn(h, make_float2(-hf.x, -hf.y)));
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&hl);
 }
 
 // Epilogue main loop of one warp.  Thread = hidden unit n; it owns rows [rh*16, rh*16+16) of both sub-tiles.
@@ -202,53 +252,120 @@ struct EpiCtx {
   float* zs; float* cs;               // &save[t = 0][row0 + rh*16][n]
   uint32_t out_row, out_step;         // element strides of `out`
   uint32_t zc_step;                   // B*H
-  int rows_left;                      // B - (row0 + rh*16): rows >= rows_left (per sub-tile offset) are padding
+  int rows_left;                      // B - first row of this thread: rows >= rows_left are padding
   int T;
-  float scale_h;
+  bool trace;
 };
 
 template <bool HAS_OUT, bool SAVE, bool MASKED>
-__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float (&hst)[TC_NT][16]) {
-  float* outp = cx.out; float* zp = cx.zs; float* cp = cx.cs;
+__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[TC_NT][4]) {
+  char* outp = reinterpret_cast<char*>(cx.out);
+  float* zp = cx.zs; float* cp = cx.cs;
+  const uint32_t row_bytes = cx.out_row * 4u;
+  const size_t tile_bytes = (size_t)TC_NS * row_bytes;
   for (int t = 0; t < cx.T; ++t) {
 #pragma unroll
     for (int s = 0; s < TC_NT; ++s) {
+      if (cx.trace) TC_TRACE(t, s, 0);
       mbar_wait(cx.bar_dfull + s * 8, t & 1);
       tc_fence_after();
+      if (cx.trace) TC_TRACE(t, s, 1);
+      float va[8], vb[8], v1[8], v2[8];
+      const uint32_t acc = cx.acc + s * TM_ACC_PER_TILE;
+      tmem_ld8(acc, va);
+      tmem_ld8(acc + TC_NS, vb);
+      tmem_ld8(acc + 2 * TC_NS, v1);
+      tmem_ld8(acc + 3 * TC_NS, v2);
+      tmem_ld_wait();
+      if (cx.trace) TC_TRACE(t, s, 2);
+      uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float vc[8], v1[8], v2[8];
-        const uint32_t acc = cx.acc + s * TM_ACC_PER_TILE + g * 8;
-        tmem_ld8(acc, vc);
-        tmem_ld8(acc + TC_NS, v1);
-        tmem_ld8(acc + 2 * TC_NS, v2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rj = s * TC_NS + g * 8 + j;                 // row offset from this thread's first row
-          const float tot = (vc[j] + v2[j]) + v1[j];
-          float z, c;
-          const float hn = gate_update(tot, hst[s][g * 8 + j], kc, z, c);
-          hst[s][g * 8 + j] = hn;
-          if (!MASKED || rj < cx.rows_left) {
-            if (HAS_OUT) outp[(uint32_t)rj * cx.out_row] = hn;
-            if (SAVE) { zp[rj * TC_H] = z; cp[rj * TC_H] = c; }
-          }
+      for (int q = 0; q < 4; ++q) {
+        const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
+        const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
+        float2 z, c;
+        hst[s][q] = gate_update2(tot, hst[s][q], kc, z, c);
+        split_pair(hst[s][q], hi[q], lo[q]);
+        if (SAVE) {                                      // training forward: z_s, c_s (cu:340-341)
+          const int rj = s * TC_NS + 2 * q;
+          if (!MASKED || rj < cx.rows_left) { zp[rj * TC_H] = z.x; cp[rj * TC_H] = c.x; }
+          if (!MASKED || rj + 1 < cx.rows_left) { zp[(rj + 1) * TC_H] = z.y; cp[(rj + 1) * TC_H] = c.y; }
         }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) split2_nc(hst[s][g * 8 + 2 * q], hst[s][g * 8 + 2 * q + 1], cx.scale_h, hi[q], lo[q]);
-        unsigned char* p = cx.hop + s * (2 * TC_NS * TC_H * 2) + g * 128;
-        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
+      unsigned char* p = cx.hop + s * (2 * TC_NS * TC_H * 2);
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (cx.trace) TC_TRACE(t, s, 3);
+      // hand h_t to the tensor core first: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would
+      // wait for the global stores too, so those are issued after the arrive and drain behind the next wait
       fence_proxy_async_smem();                        // st.shared of the h tile -> visible to tcgen05.mma
       tc_fence_before();                               // tcgen05.ld of D done before the next MMAs overwrite it
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + s * 8);
+      if (cx.trace) TC_TRACE(t, s, 4);
+      if (HAS_OUT) {
+        char* pr = outp + (s ? tile_bytes : 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rj = s * TC_NS + 2 * q;
+          if (!MASKED || rj < cx.rows_left) *reinterpret_cast<float*>(pr) = hst[s][q].x;
+          if (!MASKED || rj + 1 < cx.rows_left) *reinterpret_cast<float*>(pr + row_bytes) = hst[s][q].y;
+          pr += 2 * (size_t)row_bytes;
+        }
+      }
+      if (cx.trace) TC_TRACE(t, s, 5);
     }
-    if (HAS_OUT) outp += cx.out_step;
+    if (HAS_OUT) outp += (size_t)cx.out_step * 4u;
     if (SAVE) { zp += cx.zc_step; cp += cx.zc_step; }
+  }
+}
+
+// The 30 MMAs of one sub-tile step (K = 128 of h.U, K = 16*NKX of x.W, three fp16 products each), fully
+// unrolled, split over three issuing warps so that the serial issue latency is a third:
+//   role 0 -> CA : lo terms of x.W (W_lo.x_hi, W_hi.x_lo) and of h.U k-steps 0..2 (U_lo.h_hi, U_hi.h_lo)
+//   role 1 -> CB : lo terms of h.U k-steps 3..7
+//   role 2 -> M1 : hi.hi of x.W and of h.U k-steps 0..2;   M2 : hi.hi of h.U k-steps 3..7
+// Every TMEM column and descriptor offset is a compile-time constant on top of uniform bases.
+template <int ROLE, int NKX, bool X_HAS_LO>
+__device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
+  if (ROLE == 0) {
+#pragma unroll
+    for (int ks = 0; ks < NKX; ++ks) {
+      umma_ts(acc, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
+      if (X_HAS_LO) umma_ts(acc, tmem + TM_W_HI + ks * 8, dXlo + ks * TC_X_KSTEP, TC_IDESC_X, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+      umma_ts(acc, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+      umma_ts(acc, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+    }
+  } else if (ROLE == 1) {
+#pragma unroll
+    for (int ks = 3; ks < TC_H / 16; ++ks) {
+      umma_ts(acc + TC_NS, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+      umma_ts(acc + TC_NS, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+    }
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < NKX; ++ks) umma_ts(acc + 2 * TC_NS, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) umma_ts(acc + 2 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+#pragma unroll
+    for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts(acc + 3 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+  }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void issue_subtile_dispatch(int variant, uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
+  switch (variant) {
+    case 0: issue_subtile_mmas<ROLE, 1, false>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 1: issue_subtile_mmas<ROLE, 1, true>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 2: issue_subtile_mmas<ROLE, 2, false>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 3: issue_subtile_mmas<ROLE, 2, true>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 4: issue_subtile_mmas<ROLE, 3, false>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 5: issue_subtile_mmas<ROLE, 3, true>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    case 6: issue_subtile_mmas<ROLE, 4, false>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
+    default: issue_subtile_mmas<ROLE, 4, true>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
   }
 }
 
@@ -261,181 +378,207 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
   const TcSmemLayout L = tc_smem_layout(I, KI, esz);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
-  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [2][12] max|U|, max|W| per warp
+  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [2][16] max|U|, max|W| per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TC_ROWS;
   const bool hi_layout = a.layout == FGRNN_LAYOUT_HI;
   // barrier map
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  const int B_HREADY = 0, B_DFULL = 2, B_XFULL = 4, B_XEMPTY = 6, B_RAWFULL = 8, B_RAWEMPTY = 12;
+  const int B_HREADY = 0, B_DFULL = 2, B_XFULL = 4, B_XEMPTY = 8, B_RAWFULL = 12;   // RAWFULL: [conv warp][stage]
 
   // ---- prologue ---------------------------------------------------------------------------------
-  if (warp == 0) tmem_alloc(smem_u32(tmem_base_s), TC_TMEM_COLS);
-  if (tid == 32) {
-    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS); mbar_init(bar(B_DFULL + s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(B_XFULL + b), TC_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), 1); }
-    for (int st = 0; st < TC_RAW_STAGES; ++st) { mbar_init(bar(B_RAWFULL + st), 1); mbar_init(bar(B_RAWEMPTY + st), TC_CONV_WARPS); }
+  TC_CTA_TIME(0);
+  // warp roles: the scheduler favours high warp ids, so the latency-critical single-warp roles sit on top
+  constexpr int W_CONV0 = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + TC_CONV_WARPS;
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), TC_TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS); mbar_init(bar(B_DFULL + s), TC_MMA_WARPS); }
+    for (int b = 0; b < TC_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TC_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TC_MMA_WARPS); }
+    for (int st = 0; st < TC_CONV_WARPS * TC_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
     fence_mbar_init();
   }
-  // power-of-two operand scales from max|U|, max|W| (identical in every CTA)
-  float mu = 0.f, mw = 0.f;
-  for (int e = tid; e < TC_H * TC_H; e += TC_THREADS) mu = fmaxf(mu, fabsf(__ldg(a.U + e)));
-  for (int e = tid; e < TC_H * I; e += TC_THREADS) mw = fmaxf(mw, fabsf(__ldg(a.W + e)));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
-    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-  }
-  if (lane == 0) { red_s[warp] = mu; red_s[12 + warp] = mw; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_base_s;
-  for (int w = 0; w < TC_THREADS / 32; ++w) { mu = fmaxf(mu, red_s[w]); mw = fmaxf(mw, red_s[12 + w]); }
-  // accumulators hold 2^S * pre:  (h*2^4).(U*2^(S-4))  and  (x*2^0).(W*2^S)
-  int S = 40;
-  if (mw > 0.f) S = min(S, (int)floorf(log2f(30000.f / mw)));
-  if (mu > 0.f) S = min(S, (int)floorf(log2f(30000.f / mu)) + TC_SH_EXP);
-  S = max(S, TC_SH_EXP - 14);
-  const float scale_w = exp2f((float)S), scale_u = exp2f((float)(S - TC_SH_EXP)), scale_h = exp2f((float)TC_SH_EXP);
-  const float unscale = exp2f((float)-S);
 
-  if (warp == 0) {
-    // =========================== MMA issuer =====================================================
+  if (warp >= W_MMA) {
+    // =========================== MMA issuers (three warps, 10 MMAs each per sub-tile step) ========
+    const int role = warp - W_MMA;
     tc_fence_before();
     __syncthreads();                                   // weights in TMEM, h_{-1} / x_0 tiles under way
     tc_fence_after();
     const int nkx = KI >> 4;
     const bool x_has_lo = d.x_dtype != FGRNN_BF16;     // a bf16 value is one exact fp16 (plus an exact zero lo)
-    uint64_t dH[TC_NT][2];
-#pragma unroll
-    for (int s = 0; s < TC_NT; ++s)
-#pragma unroll
-      for (int p = 0; p < 2; ++p) dH[s][p] = make_desc_mnmajor(smem_u32(sm + L.h_op + (s * 2 + p) * TC_NS * TC_H * 2));
+    const uint64_t dH0 = make_desc_mnmajor(smem_u32(sm + L.h_op));
+    const uint32_t hlo_step = (uint32_t)(TC_NS * TC_H * 2) >> 4, htile_step = 2 * hlo_step;
+    const uint64_t dX0 = make_desc_kmajor(smem_u32(sm + L.x_op), KI);
+    const uint32_t xlo_step = (uint32_t)L.x_tile_bytes >> 4, xtile_step = 2 * xlo_step, xbuf_step = TC_NT * xtile_step;
+    const int variant = (nkx - 1) * 2 + (x_has_lo ? 1 : 0);
     for (int t = 0; t < d.T; ++t) {
-      const int xb = t & 1;
-      mbar_wait(bar(B_XFULL + xb), (t >> 1) & 1);      // x_t operand tiles written
+      const int xb = t % TC_XBUF;
+      mbar_wait(bar(B_XFULL + xb), (t / TC_XBUF) & 1); // x_t operand tiles written
 #pragma unroll
       for (int s = 0; s < TC_NT; ++s) {
-        const uint64_t dXhi = make_desc_kmajor(smem_u32(sm + L.x_op + ((xb * TC_NT + s) * 2 + 0) * L.x_tile_bytes), KI);
-        const uint64_t dXlo = make_desc_kmajor(smem_u32(sm + L.x_op + ((xb * TC_NT + s) * 2 + 1) * L.x_tile_bytes), KI);
-        const uint32_t accC = tmem + TM_ACC + s * TM_ACC_PER_TILE, accM1 = accC + TC_NS, accM2 = accC + 2 * TC_NS;
+        const uint64_t dXhi = dX0 + (uint64_t)(xb * xbuf_step + s * xtile_step), dXlo = dXhi + xlo_step;
+        const uint64_t dHhi = dH0 + (uint64_t)(s * htile_step), dHlo = dHhi + hlo_step;
+        const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
+        if (role == 0) TC_TRACE(t, s, 8);
         mbar_wait(bar(B_HREADY + s), t & 1);           // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
-        // C: the lo terms
-        uint32_t acc = 0;
-        for (int ks = 0; ks < nkx; ++ks) {
-          umma_ts(accC, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, acc); acc = 1;
-          if (x_has_lo) umma_ts(accC, tmem + TM_W_HI + ks * 8, dXlo + ks * TC_X_KSTEP, TC_IDESC_X, 1);
-        }
-#pragma unroll
-        for (int ks = 0; ks < TC_H / 16; ++ks) {
-          umma_ts(accC, tmem + TM_U_LO + ks * 8, dH[s][0] + ks * TC_H_KSTEP, TC_IDESC_H, 1);
-          umma_ts(accC, tmem + TM_U_HI + ks * 8, dH[s][1] + ks * TC_H_KSTEP, TC_IDESC_H, 1);
-        }
-        // M1: hi.hi of x.W and of the first three k-steps of h.U;  M2: the other five
-        acc = 0;
-        for (int ks = 0; ks < nkx; ++ks) { umma_ts(accM1, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, acc); acc = 1; }
-#pragma unroll
-        for (int ks = 0; ks < 3; ++ks) umma_ts(accM1, tmem + TM_U_HI + ks * 8, dH[s][0] + ks * TC_H_KSTEP, TC_IDESC_H, 1);
-#pragma unroll
-        for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts(accM2, tmem + TM_U_HI + ks * 8, dH[s][0] + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+        if (role == 0) TC_TRACE(t, s, 9);
+        if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+        else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+        else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
         umma_commit(bar(B_DFULL + s));                 // implies tcgen05.fence::before_thread_sync
+        if (role == 0) TC_TRACE(t, s, 10);
       }
-      umma_commit(bar(B_XEMPTY + xb));                 // both sub-tiles have consumed the x_t tiles
+      umma_commit(bar(B_XEMPTY + xb));                 // this warp's MMAs have consumed the x_t tiles
     }
-  } else if (warp <= TC_CONV_WARPS) {
+  } else if (warp >= W_CONV0) {
     // =========================== x path: TMA -> split -> operand tiles ============================
-    const int cw = warp - 1;
+    // Each converter warp owns 16 rows of the CTA's 64: its own TMA box, raw ring and barriers, so the four
+    // never wait for one another.  The (row, 8-feature chunk) -> address mapping is step-invariant.
+    const int cw = warp - W_CONV0;
     const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
+    unsigned char* raw_base = sm + L.raw + cw * TC_RAW_STAGES * L.raw_stage_bytes;
+    const int my_row0 = row0 + cw * TC_CONV_ROWS;
     auto issue_tma = [&](int t) {
       const int st = t % TC_RAW_STAGES;
-      mbar_expect_tx(bar(B_RAWFULL + st), raw_bytes);
-      if (ta.x_time_outer) tma_load_3d(smem_u32(sm + L.raw + st * L.raw_stage_bytes), &xmap, 0, row0, t, bar(B_RAWFULL + st));
-      else tma_load_3d(smem_u32(sm + L.raw + st * L.raw_stage_bytes), &xmap, 0, t, row0, bar(B_RAWFULL + st));
+      const uint32_t fb = bar(B_RAWFULL + cw * TC_RAW_STAGES + st);
+      mbar_expect_tx(fb, raw_bytes);
+      if (ta.x_time_outer) tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, my_row0, t, fb);
+      else tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, t, my_row0, fb);
     };
-    if (cw == 0 && lane == 0)
+    if (lane == 0)
       for (int t = 0; t < TC_RAW_STAGES && t < d.T; ++t) issue_tma(t);
     tc_fence_before();
     __syncthreads();
-    const int nch = KI >> 3, ntask = TC_ROWS * nch;
+    const int nch = KI >> 3, ntask = TC_CONV_ROWS * nch;          // <= 128 tasks: at most 4 per lane
+    constexpr int MAXIT = TC_CONV_ROWS * (TC_MAX_KI / 8) / 32;
+    uint32_t src_off[MAXIT], dst_off[MAXIT];
+    bool live[MAXIT], pad[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int e = it * 32 + lane;
+      const int row = e / nch, ch = e - row * nch;
+      live[it] = e < ntask;
+      pad[it] = ch * 8 >= I;                                     // K padding chunk: zeros
+      src_off[it] = (uint32_t)(row * I * esz + ch * 8 * esz);
+      const int R = cw * TC_CONV_ROWS + row, sidx = R / TC_NS, r = R - sidx * TC_NS;
+      dst_off[it] = (uint32_t)((sidx * 2) * L.x_tile_bytes + (r >> 3) * (nch * 128) + ch * 128 + (r & 7) * 16);
+    }
+    const uint32_t xbuf_bytes = (uint32_t)(TC_NT * 2 * L.x_tile_bytes);
     for (int t = 0; t < d.T; ++t) {
-      const int st = t % TC_RAW_STAGES, xb = t & 1;
-      mbar_wait(bar(B_RAWFULL + st), (t / TC_RAW_STAGES) & 1);
-      mbar_wait(bar(B_XEMPTY + xb), ((t >> 1) & 1) ^ 1);       // MMAs of step t-2 have finished with this buffer
-      const unsigned char* raw = sm + L.raw + st * L.raw_stage_bytes;
-      for (int e = cw * 32 + lane; e < ntask; e += TC_CONV_WARPS * 32) {
-        const int row = e / nch, ch = e - row * nch;
-        float v[8];
-        if (ch * 8 < I) {
+      const int st = t % TC_RAW_STAGES, xb = t % TC_XBUF;
+      if (cw == 0) TC_TRACE(t, 0, 12);
+      mbar_wait(bar(B_RAWFULL + cw * TC_RAW_STAGES + st), (t / TC_RAW_STAGES) & 1);
+      if (cw == 0) TC_TRACE(t, 0, 13);
+      mbar_wait(bar(B_XEMPTY + xb), ((t / TC_XBUF) & 1) ^ 1);    // MMAs of step t-XBUF have finished with this buffer
+      if (cw == 0) TC_TRACE(t, 0, 14);
+      const unsigned char* raw = raw_base + st * L.raw_stage_bytes;
+      unsigned char* xdst = sm + L.x_op + xb * xbuf_bytes;
+      float v[MAXIT][8];
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        if (live[it] && !pad[it]) {
           if (esz == 4) {
-            const float4 p0 = *reinterpret_cast<const float4*>(raw + (size_t)row * I * 4 + ch * 32);
-            const float4 p1 = *reinterpret_cast<const float4*>(raw + (size_t)row * I * 4 + ch * 32 + 16);
-            v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+            const float4 p0 = *reinterpret_cast<const float4*>(raw + src_off[it]);
+            const float4 p1 = *reinterpret_cast<const float4*>(raw + src_off[it] + 16);
+            v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w;
+            v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
           } else {
-            const uint4 p = *reinterpret_cast<const uint4*>(raw + (size_t)row * I * 2 + ch * 16);
+            const uint4 p = *reinterpret_cast<const uint4*>(raw + src_off[it]);
             const uint32_t w[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+            for (int q = 0; q < 4; ++q) { v[it][2 * q] = __uint_as_float(w[q] << 16); v[it][2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = 0.f;
+          for (int q = 0; q < 8; ++q) v[it][q] = 0.f;
         }
-        uint32_t hi[4], lo[4];
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], 1.0f, hi[q], lo[q]);
-        const int s = row / TC_NS, r = row - s * TC_NS;
-        unsigned char* xt = sm + L.x_op + ((xb * TC_NT + s) * 2) * L.x_tile_bytes + (r >> 3) * (nch * 128) + ch * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4*>(xt) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(xt + L.x_tile_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int it = 0; it < MAXIT; ++it) {
+        if (live[it]) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split2(v[it][2 * q], v[it][2 * q + 1], 1.0f, hi[q], lo[q]);
+          *reinterpret_cast<uint4*>(xdst + dst_off[it]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(xdst + dst_off[it] + L.x_tile_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
-      fence_proxy_async_smem();                        // st.shared of the operand tiles -> visible to tcgen05.mma
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(B_XFULL + xb)); mbar_arrive(bar(B_RAWEMPTY + st)); }
-      if (cw == 0 && lane == 0 && t + TC_RAW_STAGES < d.T) {
-        mbar_wait(bar(B_RAWEMPTY + st), (t / TC_RAW_STAGES) & 1);      // all converter warps are done with this stage
-        fence_proxy_async_smem();
-        issue_tma(t + TC_RAW_STAGES);
+      fence_proxy_async_smem();                        // st.shared of the operand tiles -> visible to tcgen05.mma;
+      __syncwarp();                                    // also orders this warp's raw reads before the next TMA write
+      if (lane == 0) {
+        mbar_arrive(bar(B_XFULL + xb));
+        if (t + TC_RAW_STAGES < d.T) issue_tma(t + TC_RAW_STAGES);
       }
+      if (cw == 0) TC_TRACE(t, 0, 15);
       __syncwarp();
     }
   } else {
     // =========================== epilogue warps ===================================================
-    const int ew = warp - 1 - TC_CONV_WARPS;           // 0..7
+    const int ew = warp;                               // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access (= ew & 3)
-    const int rh = ew >> 2;                            // which 16 of the sub-tile's 32 rows
+    const int rq = ew >> 2;                            // which 8 of each sub-tile's 32 rows
     const int n = quad * 32 + lane;                    // hidden unit = TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-    // weights -> tensor memory (A operands): this thread's row of U^T / W^T, fp16 hi/lo pairs along k
+    // weights -> tensor memory (A operands): this thread's row of U^T / W^T, fp16 hi/lo pairs along k.
+    // The four warps of a quadrant take 32 k each of U and 16 k each of W; everything is loaded in one batch,
+    // the power-of-two scale comes from max|U|, max|W| over the CTA's copy (identical in every CTA).
+    float scale_w, unscale;
     {
-      const int k_begin = rh * (TC_H / 2);
-      for (int kc = 0; kc < TC_H / 2; kc += 16) {
-        uint32_t hi[8], lo[8];
+      const int part = ew >> 2;                        // 0..3
+      float uv[32], wv[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = k_begin + kc + 2 * j;
-          const float v0 = hi_layout ? __ldg(a.U + (size_t)n * TC_H + k) : __ldg(a.U + (size_t)k * TC_H + n);
-          const float v1 = hi_layout ? __ldg(a.U + (size_t)n * TC_H + k + 1) : __ldg(a.U + (size_t)(k + 1) * TC_H + n);
-          split2(v0, v1, scale_u, hi[j], lo[j]);
-        }
-        tmem_st8(tmem + lane_base + TM_U_HI + ((k_begin + kc) >> 1), hi);
-        tmem_st8(tmem + lane_base + TM_U_LO + ((k_begin + kc) >> 1), lo);
+      for (int j = 0; j < 32; ++j) {
+        const int k = part * 32 + j;
+        uv[j] = hi_layout ? __ldg(a.U + (size_t)n * TC_H + k) : __ldg(a.U + (size_t)k * TC_H + n);
       }
-      for (int kc = rh * 16; kc < KI; kc += 32) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = part * 16 + j;
+        wv[j] = k < I ? (hi_layout ? __ldg(a.W + (size_t)n * I + k) : __ldg(a.W + (size_t)k * TC_H + n)) : 0.f;
+      }
+      float mu = 0.f, mw = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mu = fmaxf(mu, fabsf(uv[j]));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mw = fmaxf(mw, fabsf(wv[j]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+        mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+      }
+      if (lane == 0) { red_s[ew] = mu; red_s[16 + ew] = mw; }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // epilogue warps only
+#pragma unroll
+      for (int w = 0; w < TC_EPI_WARPS; ++w) { mu = fmaxf(mu, red_s[w]); mw = fmaxf(mw, red_s[16 + w]); }
+      // accumulators hold 2^S * pre:  h.(U*2^S) and x.(W*2^S); h and x themselves are split unscaled (an fp16
+      // subnormal lo part still resolves 2^-24 absolute, i.e. fp32-level for |h| <= 1)
+      int S = 40;
+      if (mw > 0.f) S = min(S, (int)floorf(log2f(30000.f / mw)));
+      if (mu > 0.f) S = min(S, (int)floorf(log2f(30000.f / mu)));
+      S = max(S, -14);
+      scale_w = exp2f((float)S);
+      unscale = exp2f((float)-S);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = kc + 2 * j;
-          float v0 = 0.f, v1 = 0.f;
-          if (k < I) v0 = hi_layout ? __ldg(a.W + (size_t)n * I + k) : __ldg(a.W + (size_t)k * TC_H + n);
-          if (k + 1 < I) v1 = hi_layout ? __ldg(a.W + (size_t)n * I + k + 1) : __ldg(a.W + (size_t)(k + 1) * TC_H + n);
-          split2(v0, v1, scale_w, hi[j], lo[j]);
-        }
-        tmem_st8(tmem + lane_base + TM_W_HI + (kc >> 1), hi);
-        tmem_st8(tmem + lane_base + TM_W_LO + (kc >> 1), lo);
+        for (int j = 0; j < 8; ++j) split2(uv[c * 16 + 2 * j], uv[c * 16 + 2 * j + 1], scale_w, hi[j], lo[j]);
+        tmem_st8(tmem + lane_base + TM_U_HI + part * 16 + c * 8, hi);
+        tmem_st8(tmem + lane_base + TM_U_LO + part * 16 + c * 8, lo);
+      }
+      if (part * 16 < KI) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split2(wv[2 * j], wv[2 * j + 1], scale_w, hi[j], lo[j]);
+        tmem_st8(tmem + lane_base + TM_W_HI + part * 8, hi);
+        tmem_st8(tmem + lane_base + TM_W_LO + part * 8, lo);
       }
       tmem_st_wait();
     }
@@ -444,32 +587,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     {
       const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
       constexpr float LOG2E = 1.4426950408889634f;
-      kc.kS = -LOG2E * unscale; kc.k2S = -2.0f * LOG2E * unscale;
-      kc.cg = -LOG2E * __ldg(a.bias_gate + n); kc.cu = -2.0f * LOG2E * __ldg(a.bias_update + n);
-      kc.sz = sz; kc.szn = sz + sn;
-      // tot >= tmin  <=>  both exponents <= 60
-      kc.tmin = fmaxf((60.0f - kc.cg) / kc.kS, (60.0f - kc.cu) / kc.k2S);
+      const float bgv = __ldg(a.bias_gate + n), buv = __ldg(a.bias_update + n);
+      const float kS = -LOG2E * unscale, cg = -LOG2E * bgv;
+      kc.kS = make_float2(kS, kS); kc.cg = make_float2(cg, cg);
+      kc.msz = make_float2(-sz, -sz); kc.szn = make_float2(sz + sn, sz + sn);
+#if FGRNN_TC_ONE_EX2
+      const float ratio = fminf(fmaxf(expf(2.0f * (bgv - buv)), 1e-9f), 1e9f);
+      kc.cu = make_float2(ratio, ratio); kc.k2S = kc.kS;
+      // e_g <= 2^30 keeps (1+e_g)(1+e_g^2 ratio) finite
+      kc.tmin = (30.0f - cg) / kS;
+#else
+      const float k2S = -2.0f * LOG2E * unscale, cu = -2.0f * LOG2E * buv;
+      kc.k2S = make_float2(k2S, k2S); kc.cu = make_float2(cu, cu);
+      kc.tmin = fmaxf((60.0f - cg) / kS, (60.0f - cu) / k2S);       // tot >= tmin  <=>  both exponents <= 60
+#endif
     }
 
-    // state: this thread owns h[row][n] for 16 rows of each sub-tile
-    float hst[TC_NT][16];
-    unsigned char* hop = sm + L.h_op + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
+    // state: this thread owns h[row][n] for 8 rows of each sub-tile, kept as row pairs for the fp32x2 pipe
+    float2 hst[TC_NT][4];
+    unsigned char* hop = sm + L.h_op + (n >> 3) * ((TC_NS >> 3) * 128) + rq * 128 + (n & 7) * 16;
+    const int first_row = row0 + rq * 8;
 #pragma unroll
     for (int s = 0; s < TC_NT; ++s) {
+      uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int row = row0 + s * TC_NS + rh * 16 + j;
-        hst[s][j] = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const int row = first_row + s * TC_NS + 2 * q;
+        const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
+        const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
+        hst[s][q] = make_float2(v0, v1);
+        split2(v0, v1, 1.0f, hi[q], lo[q]);
       }
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) split2(hst[s][g * 8 + 2 * q], hst[s][g * 8 + 2 * q + 1], scale_h, hi[q], lo[q]);
-        unsigned char* p = hop + s * (2 * TC_NS * TC_H * 2) + g * 128;
-        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
+      unsigned char* p = hop + s * (2 * TC_NS * TC_H * 2);
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -477,16 +628,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     __syncwarp();
     if (lane == 0) { mbar_arrive(bar(B_HREADY + 0)); mbar_arrive(bar(B_HREADY + 1)); }   // phase 0: h_{-1} ready
 
+    TC_CTA_TIME(1);
     EpiCtx cx;
     cx.bar_dfull = bar(B_DFULL); cx.bar_hready = bar(B_HREADY);
-    cx.acc = tmem + lane_base + TM_ACC + rh * 16;
+    cx.acc = tmem + lane_base + TM_ACC + rq * 8;
     cx.hop = hop;
-    const int first_row = row0 + rh * 16;
     cx.out = a.out ? a.out + (size_t)first_row * a.osb + n : nullptr;
     cx.zs = a.save_z ? a.save_z + (size_t)first_row * TC_H + n : nullptr;
     cx.cs = a.save_c ? a.save_c + (size_t)first_row * TC_H + n : nullptr;
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
-    cx.rows_left = d.B - first_row; cx.T = d.T; cx.scale_h = scale_h;
+    cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = ew == 0;
     const bool masked = row0 + TC_ROWS > d.B;
     const int variant = (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
@@ -499,19 +650,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
       case 6: epilogue_loop<true, true, false>(cx, kc, hst); break;
       default: epilogue_loop<true, true, true>(cx, kc, hst); break;
     }
+    TC_CTA_TIME(2);
     if (a.h_last) {
 #pragma unroll
       for (int s = 0; s < TC_NT; ++s)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int row = first_row + s * TC_NS + j;
-          if (row < d.B) a.h_last[(size_t)row * TC_H + n] = hst[s][j];
+          if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[s][j >> 1].y : hst[s][j >> 1].x;
         }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TC_TMEM_COLS);
+  if (warp == W_MMA) tmem_dealloc(tmem, TC_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -564,11 +716,11 @@ int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   if (ta.x_time_outer) {
     gdim[1] = (cuuint64_t)d.B; gdim[2] = (cuuint64_t)d.T;
     gstr[0] = (cuuint64_t)a.xsb * esz; gstr[1] = (cuuint64_t)a.xst * esz;
-    box[1] = TC_ROWS; box[2] = 1;
+    box[1] = TC_CONV_ROWS; box[2] = 1;
   } else {
     gdim[1] = (cuuint64_t)d.T; gdim[2] = (cuuint64_t)d.B;
     gstr[0] = (cuuint64_t)a.xst * esz; gstr[1] = (cuuint64_t)a.xsb * esz;
-    box[1] = 1; box[2] = TC_ROWS;
+    box[1] = 1; box[2] = TC_CONV_ROWS;
   }
   const CUresult cr = encode(&map, d.x_dtype == FGRNN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                              const_cast<void*>(a.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -99,7 +99,8 @@ def run(seed, scheme, T=99, B=64, h0_given=False, wscale=0.1, SU=8, SW=12, SH=4,
 if __name__ == '__main__':
     schemes = sys.argv[1].split(',') if len(sys.argv) > 1 else ['single', 'main1', 'main2', 'main5', 'main10']
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 99
+    SH = int(sys.argv[3]) if len(sys.argv) > 3 else 4
     for sc in schemes:
         for seed in (0, 1):
             for h0g in (False, True):
-                print(sc, 'seed', seed, 'h0', int(h0g), 'vs-oracle %.3f vs-truth %.3f' % run(seed, sc, T=T, h0_given=h0g), flush=True)
+                print(sc, 'seed', seed, 'h0', int(h0g), 'vs-oracle %.3f vs-truth %.3f' % run(seed, sc, T=T, h0_given=h0g, SH=SH, SU=12 - SH), flush=True)
