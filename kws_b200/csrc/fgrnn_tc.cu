@@ -41,7 +41,7 @@ constexpr int TC_ROWS = TC_NS * TC_NT;         // 64 batch rows per CTA
 constexpr int TC_CONV_WARPS = 4;                // each owns 16 rows of the x tile: own TMA box, own raw ring
 constexpr int TC_CONV_ROWS = 16;
 constexpr int TC_XBUF = 4;                      // x operand tile buffers (the converters run up to 3 steps ahead)
-constexpr int TC_EPI_WARPS = 16;                // 4 TMEM lane quadrants x 4 row groups (8 rows of EACH sub-tile)
+constexpr int TC_EPI_WARPS = 16;                // 8 per sub-tile: 4 TMEM lane quadrants x 2 row halves
 constexpr int TC_MMA_WARPS = 3;                 // the 30 MMAs of a sub-tile step are issued by three warps, 10 each
 constexpr int TC_THREADS = 32 * (TC_MMA_WARPS + TC_CONV_WARPS + TC_EPI_WARPS);   // 736
 constexpr int TC_RAW_STAGES = 4;
@@ -50,6 +50,9 @@ constexpr int TC_MAX_KI = 64;                  // input features padded to a mul
 constexpr int TM_U_HI = 0, TM_U_LO = 64, TM_W_HI = 128, TM_W_LO = 160, TM_ACC = 192;
 constexpr int TM_ACC_PER_TILE = 4 * TC_NS;     // CA | CB | M1 | M2
 constexpr int TC_TMEM_COLS = 512;
+#ifndef TC_STAGGER_NS
+#define TC_STAGGER_NS 500
+#endif
 
 // Developer trace (tools/tc_trace.cu defines FGRNN_TC_TRACE): clock64 stamps of CTA 0 for steps [16, 20)
 #ifdef FGRNN_TC_TRACE
@@ -108,6 +111,20 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// same, for code that already runs on one elected lane only
+__device__ __forceinline__ void umma_ts1(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit1(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // arrives on the mbarrier when every MMA issued so far by the elected lane has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -253,69 +270,67 @@ struct EpiCtx {
   uint32_t out_row, out_step;         // element strides of `out`
   uint32_t zc_step;                   // B*H
   int rows_left;                      // B - first row of this thread: rows >= rows_left are padding
-  int T;
+  int T, s;
   bool trace;
 };
 
 template <bool HAS_OUT, bool SAVE, bool MASKED>
-__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[TC_NT][4]) {
+__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[8]) {
   char* outp = reinterpret_cast<char*>(cx.out);
   float* zp = cx.zs; float* cp = cx.cs;
   const uint32_t row_bytes = cx.out_row * 4u;
-  const size_t tile_bytes = (size_t)TC_NS * row_bytes;
   for (int t = 0; t < cx.T; ++t) {
+    if (cx.trace) TC_TRACE(t, cx.s, 0);
+    mbar_wait(cx.bar_dfull, t & 1);
+    tc_fence_after();
+    if (cx.trace) TC_TRACE(t, cx.s, 1);
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int s = 0; s < TC_NT; ++s) {
-      if (cx.trace) TC_TRACE(t, s, 0);
-      mbar_wait(cx.bar_dfull + s * 8, t & 1);
-      tc_fence_after();
-      if (cx.trace) TC_TRACE(t, s, 1);
+    for (int g = 0; g < 2; ++g) {
       float va[8], vb[8], v1[8], v2[8];
-      const uint32_t acc = cx.acc + s * TM_ACC_PER_TILE;
-      tmem_ld8(acc, va);
-      tmem_ld8(acc + TC_NS, vb);
-      tmem_ld8(acc + 2 * TC_NS, v1);
-      tmem_ld8(acc + 3 * TC_NS, v2);
+      tmem_ld8(cx.acc + g * 8, va);
+      tmem_ld8(cx.acc + TC_NS + g * 8, vb);
+      tmem_ld8(cx.acc + 2 * TC_NS + g * 8, v1);
+      tmem_ld8(cx.acc + 3 * TC_NS + g * 8, v2);
       tmem_ld_wait();
-      if (cx.trace) TC_TRACE(t, s, 2);
-      uint32_t hi[4], lo[4];
+      if (cx.trace && g == 0) TC_TRACE(t, cx.s, 2);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
         const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
         float2 z, c;
-        hst[s][q] = gate_update2(tot, hst[s][q], kc, z, c);
-        split_pair(hst[s][q], hi[q], lo[q]);
+        hst[g * 4 + q] = gate_update2(tot, hst[g * 4 + q], kc, z, c);
+        split_pair(hst[g * 4 + q], hi[g * 4 + q], lo[g * 4 + q]);
         if (SAVE) {                                      // training forward: z_s, c_s (cu:340-341)
-          const int rj = s * TC_NS + 2 * q;
+          const int rj = g * 8 + 2 * q;
           if (!MASKED || rj < cx.rows_left) { zp[rj * TC_H] = z.x; cp[rj * TC_H] = c.x; }
           if (!MASKED || rj + 1 < cx.rows_left) { zp[(rj + 1) * TC_H] = z.y; cp[(rj + 1) * TC_H] = c.y; }
         }
       }
-      unsigned char* p = cx.hop + s * (2 * TC_NS * TC_H * 2);
-      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (cx.trace) TC_TRACE(t, s, 3);
-      // hand h_t to the tensor core first: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would
-      // wait for the global stores too, so those are issued after the arrive and drain behind the next wait
-      fence_proxy_async_smem();                        // st.shared of the h tile -> visible to tcgen05.mma
-      tc_fence_before();                               // tcgen05.ld of D done before the next MMAs overwrite it
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + s * 8);
-      if (cx.trace) TC_TRACE(t, s, 4);
-      if (HAS_OUT) {
-        char* pr = outp + (s ? tile_bytes : 0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int rj = s * TC_NS + 2 * q;
-          if (!MASKED || rj < cx.rows_left) *reinterpret_cast<float*>(pr) = hst[s][q].x;
-          if (!MASKED || rj + 1 < cx.rows_left) *reinterpret_cast<float*>(pr + row_bytes) = hst[s][q].y;
-          pr += 2 * (size_t)row_bytes;
-        }
-      }
-      if (cx.trace) TC_TRACE(t, s, 5);
     }
-    if (HAS_OUT) outp += (size_t)cx.out_step * 4u;
+    *reinterpret_cast<uint4*>(cx.hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(cx.hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    if (cx.trace) TC_TRACE(t, cx.s, 3);
+    // hand h_t to the tensor core first: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would
+    // wait for the global stores too, so those are issued after the arrive and drain behind the next wait
+    fence_proxy_async_smem();                          // st.shared of the h tile -> visible to tcgen05.mma
+    tc_fence_before();                                 // tcgen05.ld of D done before the next MMAs overwrite it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready);
+    if (cx.trace) TC_TRACE(t, cx.s, 4);
+    if (HAS_OUT) {
+      char* pr = outp;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(pr) = hst[q].x;
+        if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(pr + row_bytes) = hst[q].y;
+        pr += 2 * (size_t)row_bytes;
+      }
+      outp += (size_t)cx.out_step * 4u;
+    }
+    if (cx.trace) TC_TRACE(t, cx.s, 5);
     if (SAVE) { zp += cx.zc_step; cp += cx.zc_step; }
   }
 }
@@ -331,27 +346,27 @@ __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, 
   if (ROLE == 0) {
 #pragma unroll
     for (int ks = 0; ks < NKX; ++ks) {
-      umma_ts(acc, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
-      if (X_HAS_LO) umma_ts(acc, tmem + TM_W_HI + ks * 8, dXlo + ks * TC_X_KSTEP, TC_IDESC_X, 1);
+      umma_ts1(acc, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
+      if (X_HAS_LO) umma_ts1(acc, tmem + TM_W_HI + ks * 8, dXlo + ks * TC_X_KSTEP, TC_IDESC_X, 1);
     }
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) {
-      umma_ts(acc, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
-      umma_ts(acc, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+      umma_ts1(acc, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+      umma_ts1(acc, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
     }
   } else if (ROLE == 1) {
 #pragma unroll
     for (int ks = 3; ks < TC_H / 16; ++ks) {
-      umma_ts(acc + TC_NS, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
-      umma_ts(acc + TC_NS, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+      umma_ts1(acc + TC_NS, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+      umma_ts1(acc + TC_NS, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
     }
   } else {
 #pragma unroll
-    for (int ks = 0; ks < NKX; ++ks) umma_ts(acc + 2 * TC_NS, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
+    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc + 2 * TC_NS, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < 3; ++ks) umma_ts(acc + 2 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+    for (int ks = 0; ks < 3; ++ks) umma_ts1(acc + 2 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
 #pragma unroll
-    for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts(acc + 3 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+    for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts1(acc + 3 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
   }
 }
 
@@ -393,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
   constexpr int W_CONV0 = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + TC_CONV_WARPS;
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), TC_TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS); mbar_init(bar(B_DFULL + s), TC_MMA_WARPS); }
+    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS / TC_NT); mbar_init(bar(B_DFULL + s), TC_MMA_WARPS); }
     for (int b = 0; b < TC_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TC_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TC_MMA_WARPS); }
     for (int st = 0; st < TC_CONV_WARPS * TC_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
     fence_mbar_init();
@@ -401,11 +416,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_base_s;
+  // The CTA owns all 512 columns, so the allocation starts at TMEM address 0; using the constant keeps every
+  // tcgen05 address warp-uniform (no R2UR in the MMA issue path).
+  if (*tmem_base_s != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
 
   if (warp >= W_MMA) {
     // =========================== MMA issuers (three warps, 10 MMAs each per sub-tile step) ========
     const int role = warp - W_MMA;
+    const bool leader = elect_one();                   // the same lane issues every MMA and commit of this warp
     tc_fence_before();
     __syncthreads();                                   // weights in TMEM, h_{-1} / x_0 tiles under way
     tc_fence_after();
@@ -428,13 +447,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         mbar_wait(bar(B_HREADY + s), t & 1);           // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
         if (role == 0) TC_TRACE(t, s, 9);
-        if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
-        else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
-        else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
-        umma_commit(bar(B_DFULL + s));                 // implies tcgen05.fence::before_thread_sync
+        if (leader) {
+          if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          umma_commit1(bar(B_DFULL + s));              // implies tcgen05.fence::before_thread_sync
+        }
+        __syncwarp();
         if (role == 0) TC_TRACE(t, s, 10);
+        // start the two sub-tile pipelines half a period apart so that one is in its MMA phase while the
+        // other is in its epilogue (they keep the offset: nothing couples them but shared pipes)
+        if (t == 0 && s == 0) __nanosleep(TC_STAGGER_NS);
       }
-      umma_commit(bar(B_XEMPTY + xb));                 // this warp's MMAs have consumed the x_t tiles
+      if (leader) umma_commit1(bar(B_XEMPTY + xb));    // this warp's MMAs have consumed the x_t tiles
+      __syncwarp();
     }
   } else if (warp >= W_CONV0) {
     // =========================== x path: TMA -> split -> operand tiles ============================
@@ -522,7 +548,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     // =========================== epilogue warps ===================================================
     const int ew = warp;                               // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access (= ew & 3)
-    const int rq = ew >> 2;                            // which 8 of each sub-tile's 32 rows
+    const int es = (ew >> 2) & 1;                      // the sub-tile this warp serves
+    const int rh = ew >> 3;                            // which 16 of the sub-tile's 32 rows
     const int n = quad * 32 + lane;                    // hidden unit = TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
@@ -603,41 +630,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
 #endif
     }
 
-    // state: this thread owns h[row][n] for 8 rows of each sub-tile, kept as row pairs for the fp32x2 pipe
-    float2 hst[TC_NT][4];
-    unsigned char* hop = sm + L.h_op + (n >> 3) * ((TC_NS >> 3) * 128) + rq * 128 + (n & 7) * 16;
-    const int first_row = row0 + rq * 8;
+    // state: this thread owns h[row][n] for 16 rows of its sub-tile, kept as row pairs for the fp32x2 pipe
+    float2 hst[8];
+    unsigned char* hop = sm + L.h_op + es * (2 * TC_NS * TC_H * 2) + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
+    const int first_row = row0 + es * TC_NS + rh * 16;
+    {
+      uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int s = 0; s < TC_NT; ++s) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = first_row + s * TC_NS + 2 * q;
+      for (int q = 0; q < 8; ++q) {
+        const int row = first_row + 2 * q;
         const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
         const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
-        hst[s][q] = make_float2(v0, v1);
+        hst[q] = make_float2(v0, v1);
         split2(v0, v1, 1.0f, hi[q], lo[q]);
       }
-      unsigned char* p = hop + s * (2 * TC_NS * TC_H * 2);
-      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(p + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();                                   // matches the other roles' prologue barrier
     __syncwarp();
-    if (lane == 0) { mbar_arrive(bar(B_HREADY + 0)); mbar_arrive(bar(B_HREADY + 1)); }   // phase 0: h_{-1} ready
+    if (lane == 0) mbar_arrive(bar(B_HREADY + es));    // phase 0: h_{-1} ready
 
     TC_CTA_TIME(1);
     EpiCtx cx;
-    cx.bar_dfull = bar(B_DFULL); cx.bar_hready = bar(B_HREADY);
-    cx.acc = tmem + lane_base + TM_ACC + rq * 8;
+    cx.bar_dfull = bar(B_DFULL + es); cx.bar_hready = bar(B_HREADY + es);
+    cx.acc = tmem + lane_base + TM_ACC + es * TM_ACC_PER_TILE + rh * 16;
     cx.hop = hop;
     cx.out = a.out ? a.out + (size_t)first_row * a.osb + n : nullptr;
     cx.zs = a.save_z ? a.save_z + (size_t)first_row * TC_H + n : nullptr;
     cx.cs = a.save_c ? a.save_c + (size_t)first_row * TC_H + n : nullptr;
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
-    cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = ew == 0;
+    cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = (ew & 11) == 0; cx.s = es;
     const bool masked = row0 + TC_ROWS > d.B;
     const int variant = (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
@@ -653,12 +680,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     TC_CTA_TIME(2);
     if (a.h_last) {
 #pragma unroll
-      for (int s = 0; s < TC_NT; ++s)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int row = first_row + s * TC_NS + j;
-          if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[s][j >> 1].y : hst[s][j >> 1].x;
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int row = first_row + j;
+        if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
+      }
     }
   }
   tc_fence_before();

@@ -64,7 +64,7 @@ def test_tcgen05_time_major_and_saved_gates():
 def test_tcgen05_bf16_input_and_weight_scales():
     out, _, ref, _, _ = _run(96, 20, 32, "IH", True, seed=5, x_bf16=True)
     assert state_ratio(out, ref) <= 1.0
-    for ws in (0.2, 3.0):             # power-of-two operand scaling adapts to the weight magnitude
+    for ws in (0.05, 0.2, 2.0):       # power-of-two operand scaling adapts to the weight magnitude
         out, _, ref, _, _ = _run(40, 6, 32, "HI", False, seed=6, wscale=ws)
         assert state_ratio(out, ref) <= 1.0, ws
 

@@ -60,7 +60,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return (1u << 
 constexpr int A_COL = 256;     // TMEM column where the A operand starts (D at column 0)
 
 // mode 0: correctness (n_mma = K/16 chained);  mode 1/2: timing with issue style (1 = single thread, 2 = elect)
-__global__ void __launch_bounds__(128, 1) ts_kernel(const __half* A, const __half* B, float* D, long long* tout, int K, int N, int mode, int n_mma) {
+__global__ void __launch_bounds__(128, 1) ts_kernel(const __half* A, const __half* B, float* D, long long* tout, int K, int N, int mode, int n_mma, int nacc) {
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_s;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128, 1) ts_kernel(const __half* A, const __hal
       t0 = clock64();
       for (int i = 0; i < n_mma; i += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) umma_ts_elect(tmem + (uint32_t)((j & 1) * 128), tmem + A_COL + j * 8, dB + j * kstep, idesc, 1);
+        for (int j = 0; j < 8; ++j) umma_ts_elect(tmem + (uint32_t)((j % nacc) * 32), tmem + A_COL + j * 8, dB + j * kstep, idesc, 1);
       }
       if (lane == 0) umma_commit(smem_u32(&bar));
       __syncwarp();
@@ -153,7 +153,7 @@ int main() {
     CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
     const size_t smem = 64 * 1024;
     CK(cudaFuncSetAttribute(ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ts_kernel<<<1, 128, smem>>>(dA, dB, dD, dT, K, N, 0, 0);
+    ts_kernel<<<1, 128, smem>>>(dA, dB, dD, dT, K, N, 0, 0, 1);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0;
@@ -164,12 +164,12 @@ int main() {
         maxerr = std::fmax(maxerr, std::fabs(s - (double)D[m * N + n]));
       }
     printf("TS N=%3d K=%d : max |D - exact| = %.3e  (%s)\n", N, K, maxerr, maxerr < 1e-4 ? "layout OK" : "LAYOUT WRONG");
-    for (int mode : {1, 2})
-      for (int n_mma : {8, 64, 256}) {
+    for (int nacc : {1, 2, 4})
+      for (int n_mma : {8, 32, 256}) {
         long long h[2];
-        for (int rep = 0; rep < 2; ++rep) { ts_kernel<<<1, 128, smem>>>(dA, dB, dD, dT, K, N, mode, n_mma); CK(cudaDeviceSynchronize()); }
+        for (int rep = 0; rep < 2; ++rep) { ts_kernel<<<1, 128, smem>>>(dA, dB, dD, dT, K, N, 2, n_mma, nacc); CK(cudaDeviceSynchronize()); }
         CK(cudaMemcpy(h, dT, 16, cudaMemcpyDeviceToHost));
-        printf("TS-TIME N=%3d style=%s n_mma=%3d : total %6lld cyc (%.1f/mma)  issue %6lld cyc (%.1f/mma)\n", N, mode == 1 ? "tid0 " : "elect", n_mma, h[0], (double)h[0] / n_mma, h[1], (double)h[1] / n_mma);
+        printf("TS-TIME N=%3d accumulators=%d n_mma=%3d : total %6lld cyc (%.1f/mma)  issue %6lld cyc (%.1f/mma)\n", N, nacc, n_mma, h[0], (double)h[0] / n_mma, h[1], (double)h[1] / n_mma);
       }
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dT);
   }
