@@ -149,6 +149,7 @@ struct BwdPlan {
   int path;
   int nchunk, rows_per_chunk, nrec, rows_per_cta;
   bool want_w, want_u;
+  bool tc_contract;           // dW / dU sums on the tensor cores (fgrnn_tc_bwd.cu), one partial per CTA
   float *UT, *U2T, *U1T;      // workspace copies (nullptr => use caller's pointer directly)
   float *Wf;                  // canonical [I][H] for d_x (nullptr => caller's W usable directly)
   float *dpre, *rec_partial, *partW, *partU, *dWc, *dUc;
@@ -161,6 +162,16 @@ bool smem_bwd_ok(const FgrnnBackward& g) {
   return aligned16(p.U) && aligned16(p.h0) && aligned16(g.grad_h) && mult4(g.grad_stride_b) && mult4(g.grad_stride_t) &&
          aligned16(g.hs) && mult4(g.hs_stride_b) && mult4(g.hs_stride_t) && aligned16(g.z_s) && aligned16(g.c_s) &&
          aligned16(g.d_h0);
+}
+
+// the tcgen05 contraction streams 32-byte row segments with 16-byte vector loads
+bool tc_contract_ok(const FgrnnBackward& g) {
+  const FgrnnProblem& p = g.p;
+  if (p.force_path == FGRNN_PATH_GENERIC || p.force_path == FGRNN_PATH_SMEM) return false;   // keep the FFMA kernels testable
+  if (!tc_contract_supports(dims_of(p))) return false;
+  const int64_t xm = p.x_dtype == FGRNN_BF16 ? 8 : 4;
+  return aligned16(p.x) && p.x_stride_b % xm == 0 && p.x_stride_t % xm == 0 && aligned16(g.hs) && mult4(g.hs_stride_b) &&
+         mult4(g.hs_stride_t) && aligned16(p.h0);
 }
 
 int select_bwd_path(const FgrnnBackward& g) {
@@ -181,6 +192,8 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   pl.nrec = pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p)) : gen_bwd_rec_ctas(dims_of(p));
   pl.want_w = g.d_W || g.d_W1 || g.d_W2;
   pl.want_u = g.d_U || g.d_U1 || g.d_U2;
+  pl.tc_contract = tc_contract_ok(g);
+  if (pl.tc_contract) pl.nchunk = tc_contract_ctas(dims_of(p));
   Carver cv(ws);
   const bool ih = p.weight_layout == FGRNN_LAYOUT_IH;
   if (ih && pl.path == FGRNN_PATH_GENERIC) {
@@ -440,6 +453,14 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   }
 
   // 3. T-parallel outer-product sums as per-chunk partials (no atomics)
+  if (pl.tc_contract && (pl.want_w || pl.want_u)) {
+    TcContractLaunch c{};
+    c.d = dims_of(p);
+    c.x = p.x; c.xsb = p.x_stride_b; c.xst = p.x_stride_t;
+    c.hs = g->hs; c.hsb = g->hs_stride_b; c.hst = g->hs_stride_t; c.h0 = p.h0;
+    c.dpre = pl.dpre; c.partW = pl.want_w ? pl.partW : nullptr; c.partU = pl.want_u ? pl.partU : nullptr;
+    if ((rc = launch_tc_contract(c, stream))) return rc;
+  } else {
   if (pl.want_w) {
     TnArgs t{};
     t.M = (int)M; t.B = p.B; t.T = p.T; t.K = p.I; t.N = p.H;
@@ -453,6 +474,7 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
     t.a = g->hs; t.asb = g->hs_stride_b; t.ast = g->hs_stride_t; t.a_dtype = FGRNN_F32; t.a_shift = 1; t.a_h0 = p.h0;
     t.dpre = pl.dpre; t.partial = pl.partU; t.rows_per_chunk = pl.rows_per_chunk;
     if ((rc = launch_gemm_tn_partial(t, pl.nchunk, stream))) return rc;
+  }
   }
 
   // 4. deterministic tree/linear reduce of all partials

@@ -115,4 +115,18 @@ bool tc_path_supports(const Dims& d);
 bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, int T);
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream);
 
+// T-parallel contractions dW, dU on the tensor cores (fgrnn_tc_bwd.cu); partials in the canonical orientation,
+// one per CTA, summed by launch_reduce
+struct TcContractLaunch {
+  Dims d;
+  const void* x; int64_t xsb, xst;
+  const float* hs; int64_t hsb, hst;
+  const float* h0;
+  const float* dpre;
+  float *partW, *partU;
+};
+bool tc_contract_supports(const Dims& d);
+int tc_contract_ctas(const Dims& d);
+int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream);
+
 }  // namespace fgrnn

@@ -80,3 +80,44 @@ def test_tcgen05_matches_ffma_path_on_a_full_wave():
     b = engine.forward(x, params, None, layout="IH", batch_first=True, force_path=_lib.PATH_SMEM)[0]
     torch.cuda.synchronize()
     assert state_ratio(a, b.cpu()) <= 1.0
+
+
+@pytest.mark.parametrize("B,T,I,layout,h0_given,bf", [
+    (64, 5, 32, "IH", True, True),
+    (77, 9, 32, "HI", True, True),        # ragged chunk
+    (130, 7, 16, "IH", False, False),     # three row blocks per step, time-major, I = 16
+    (33, 3, 64, "HI", True, True),        # I = 64
+    (2048, 4, 32, "IH", False, True),     # more chunks than one wave of CTAs would take alone: 128 chunks
+])
+def test_tcgen05_backward_against_autograd(B, T, I, layout, h0_given, bf):
+    """Default (auto) backward: reverse recurrence + dW/dU contractions on the tensor cores (bf16 hi/lo split,
+    per-CTA partials, fixed-order reduce) against CPU autograd of the oracle, all 12 gradient slots."""
+    from kws_b200 import engine
+    from gpu_helpers import grad_ratio
+    torch.manual_seed(B + T)
+    p = O.init_params(I, 128)
+    p.bias_gate.add_(0.2 * torch.randn(1, 128)); p.zeta.add_(0.3); p.nu.add_(0.5)
+    x = torch.randn(B, T, I)
+    h0 = 0.5 * torch.randn(B, 128) if h0_given else None
+    go = torch.randn(B, T, 128) / B                       # mean-loss sized gradients (tiny for large B)
+    gref = O.autograd_grads(x, p, h0 if h0 is not None else torch.zeros(B, 128), go, True)
+    tens = p.tensors() if layout == "IH" else O.to_cuda_layout(p)
+    params = {k: v.to(dev()).contiguous() for k, v in tens.items()}
+    xg, gog = x.to(dev()), go.to(dev())
+    if not bf:
+        xg, gog = xg.transpose(0, 1).contiguous(), gog.transpose(0, 1).contiguous()
+    h0g = None if h0 is None else h0.to(dev())
+    out, z_s, c_s, _ = engine.forward(xg, params, h0g, layout=layout, batch_first=bf, save_for_backward=True)
+    g = engine.backward(gog, xg, out, z_s, c_s, params, h0g, layout=layout, batch_first=bf)
+    torch.cuda.synchronize()
+    for k in p.tensors():
+        r = gref[k].t() if (layout == "HI" and k in ("W", "U")) else gref[k]
+        assert grad_ratio(g[k], r) <= 1.0, (k, grad_ratio(g[k], r))
+    gx = g["x"] if bf else g["x"].transpose(0, 1)
+    assert grad_ratio(gx, gref["x"]) <= 1.0
+    if h0_given:
+        assert grad_ratio(g["h0"], gref["h0"]) <= 1.0
+    # run-to-run identical (no atomics anywhere)
+    g2 = engine.backward(gog, xg, out, z_s, c_s, params, h0g, layout=layout, batch_first=bf)
+    torch.cuda.synchronize()
+    assert all(torch.equal(g[k], g2[k]) for k in ("W", "U", "bias_gate", "zeta"))
