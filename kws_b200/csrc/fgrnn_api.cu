@@ -74,6 +74,9 @@ struct DeviceGuard {
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) return;
     if (prev != dev && cudaSetDevice(dev) != cudaSuccess) return;
+    // bind the primary context to this thread: the driver-API tensor-map encoder (cuTensorMapEncodeTiled) returns
+    // CUDA_ERROR_INVALID_CONTEXT on threads that never touched the runtime (autograd worker threads)
+    if (cudaFree(nullptr) != cudaSuccess) return;
     ok = true;
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
@@ -174,8 +177,17 @@ bool tc_contract_ok(const FgrnnBackward& g) {
          mult4(g.hs_stride_t) && aligned16(p.h0);
 }
 
+// tcgen05 reverse recurrence: 512-byte bulk row copies need 16-byte aligned rows
+bool tc_bwd_ok(const FgrnnBackward& g) {
+  const FgrnnProblem& p = g.p;
+  if (!tc_bwd_rec_supports(dims_of(p))) return false;
+  return aligned16(p.U) && aligned16(p.h0) && aligned16(g.grad_h) && mult4(g.grad_stride_b) && mult4(g.grad_stride_t) &&
+         aligned16(g.hs) && mult4(g.hs_stride_b) && mult4(g.hs_stride_t) && aligned16(g.z_s) && aligned16(g.c_s);
+}
+
 int select_bwd_path(const FgrnnBackward& g) {
   if (g.p.force_path >= 0) return g.p.force_path;
+  if (tc_bwd_ok(g)) return FGRNN_PATH_TCGEN05;
   return smem_bwd_ok(g) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
 }
 
@@ -189,7 +201,8 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   pl.rows_per_chunk = (pl.rows_per_chunk + 15) / 16 * 16;
   if (pl.rows_per_chunk < 16) pl.rows_per_chunk = 16;
   pl.rows_per_cta = pl.path == FGRNN_PATH_SMEM ? smem_rows_per_cta(dims_of(p), 1) : 0;
-  pl.nrec = pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p)) : gen_bwd_rec_ctas(dims_of(p));
+  pl.nrec = pl.path == FGRNN_PATH_TCGEN05 ? tc_bwd_rec_ctas(dims_of(p))
+          : pl.path == FGRNN_PATH_SMEM ? smem_bwd_rec_ctas(dims_of(p)) : gen_bwd_rec_ctas(dims_of(p));
   pl.want_w = g.d_W || g.d_W1 || g.d_W2;
   pl.want_u = g.d_U || g.d_U1 || g.d_U2;
   pl.tc_contract = tc_contract_ok(g);
@@ -222,8 +235,8 @@ int validate_backward(const FgrnnBackward& g) {
   const int path = select_bwd_path(g);
   if (path == FGRNN_PATH_SMEM && !smem_bwd_ok(g))
     return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
-  if (path == FGRNN_PATH_TCGEN05)
-    return fail(FGRNN_ERR_SHAPE, "backward path %d not available for this shape", path);
+  if (path == FGRNN_PATH_TCGEN05 && !tc_bwd_ok(g))
+    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, sigmoid gate / tanh update and 16-byte aligned rows");
   return FGRNN_OK;
 }
 
@@ -405,8 +418,8 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
     jobs.job[jobs.n++] = PrepJob{src, dst, rows, cols, tr};
   };
   const float *UT = nullptr, *U2T = nullptr, *U1T = nullptr, *Wf = nullptr;
-  if (pl.path == FGRNN_PATH_SMEM) {
-    // the persistent kernel transposes U on its way into shared memory
+  if (pl.path == FGRNN_PATH_SMEM || pl.path == FGRNN_PATH_TCGEN05) {
+    // the persistent kernels read U in the caller's layout
   } else if (ih) {
     if (p.rU == 0) { add(p.U, pl.UT, p.H, p.H, 1); UT = pl.UT; }
     else { add(p.U2, pl.U2T, p.rU, p.H, 1); add(p.U1, pl.U1T, p.H, p.rU, 1); U2T = pl.U2T; U1T = pl.U1T; }
@@ -432,14 +445,14 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   }
 
   // 2. serial reverse recurrence
-  if (pl.path == FGRNN_PATH_SMEM) {
+  if (pl.path == FGRNN_PATH_SMEM || pl.path == FGRNN_PATH_TCGEN05) {
     SmemBwdArgs s{};
     s.d = dims_of(p); s.layout = p.weight_layout; s.U = p.U; s.zeta = p.zeta; s.nu = p.nu;
     s.grad_h = g->grad_h; s.gsb = g->grad_stride_b; s.gst = g->grad_stride_t;
     s.hs = g->hs; s.hsb = g->hs_stride_b; s.hst = g->hs_stride_t;
     s.h0 = p.h0; s.z_s = g->z_s; s.c_s = g->c_s;
     s.dpre_ws = pl.dpre; s.rec_partial = pl.rec_partial; s.d_h0 = g->d_h0;
-    if ((rc = launch_smem_bwd_rec(s, stream))) return rc;
+    if ((rc = pl.path == FGRNN_PATH_TCGEN05 ? launch_tc_bwd_rec(s, stream) : launch_smem_bwd_rec(s, stream))) return rc;
   } else {
   BwdRecArgs r{};
   r.d = dims_of(p);

@@ -448,21 +448,35 @@ int launch_small_gemm(const SmallGemm& g, cudaStream_t stream) {
 //   job 2: d_bias_gate, d_bias_update, d_zeta, d_nu <- sum over recurrence CTAs
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   const int job = blockIdx.y;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
   if (job < 2) {
+    // 32 consecutive elements per block, the partials split over 8 thread groups; both sums run in a fixed
+    // order, so the result is identical from run to run
+    __shared__ float part_s[8][33];
     const float* P = job == 0 ? a.partW : a.partU;
     float* dst = job == 0 ? a.dWc : a.dUc;
     const int K = job == 0 ? a.I : a.H;
     const int transpose = job == 0 ? a.dW_transpose : a.dU_transpose;
     if (dst == nullptr) return;
     const int total = K * a.H;
-    for (int e = gtid; e < total; e += gstride) {
+    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (int e0 = blockIdx.x * 32; e0 < total; e0 += gridDim.x * 32) {
+      const int e = e0 + el;
       float s = 0.0f;
-      for (int c = 0; c < a.nchunk; ++c) s += P[(size_t)c * total + e];
-      if (transpose) { const int k = e / a.H, n = e - k * a.H; dst[(size_t)n * K + k] = s; }
-      else dst[e] = s;
+      if (e < total)
+        for (int c = grp; c < a.nchunk; c += 8) s += P[(size_t)c * total + e];
+      part_s[grp][el] = s;
+      __syncthreads();
+      if (grp == 0 && e < total) {
+        float r = part_s[0][el];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) r += part_s[g][el];
+        if (transpose) { const int k = e / a.H, n = e - k * a.H; dst[(size_t)n * K + k] = r; }
+        else dst[e] = r;
+      }
+      __syncthreads();
     }
   } else {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     const int stride = 2 * a.H + 2;
     for (int e = gtid; e < stride; e += gstride) {
       float s = 0.0f;
@@ -481,7 +495,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
 }
 
 int launch_reduce(const ReduceArgs& a, cudaStream_t stream) {
-  dim3 grid(32, 3);
+  dim3 grid(256, 3);
   reduce_kernel<<<grid, 256, 0, stream>>>(a);
   FGRNN_LAUNCH_CHECK("reduce_kernel");
   return FGRNN_OK;

@@ -125,6 +125,9 @@ struct TcContractLaunch {
   const float* dpre;
   float *partW, *partU;
 };
+bool tc_bwd_rec_supports(const Dims& d);
+int tc_bwd_rec_ctas(const Dims& d);
+int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 bool tc_contract_supports(const Dims& d);
 int tc_contract_ctas(const Dims& d);
 int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream);

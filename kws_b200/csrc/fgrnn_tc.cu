@@ -592,20 +592,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
 bool tc_path_supports(const Dims& d) {
   // full-rank, H = 128, I a multiple of 8 up to 64, sigmoid gate / tanh update
   return d.rW == 0 && d.rU == 0 && d.H == TC_H && d.I >= 8 && d.I <= TC_MAX_KI && (d.I % 8) == 0 &&
@@ -624,31 +610,13 @@ bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, in
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   const Dims& d = a.d;
   if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
-  EncodeTiledFn encode = encode_tiled_fn();
-  if (!encode) { set_error_detail("cuTensorMapEncodeTiled is not available from the driver"); return FGRNN_ERR_CUDA; }
   TcArgs ta{};
   ta.f = a;
   ta.KI = (d.I + 15) & ~15;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
-  ta.x_time_outer = a.xst > a.xsb ? 1 : 0;
   CUtensorMap map;
-  cuuint64_t gdim[3], gstr[2];
-  cuuint32_t box[3], estr[3] = {1, 1, 1};
-  gdim[0] = (cuuint64_t)d.I;
-  box[0] = (cuuint32_t)d.I;
-  if (ta.x_time_outer) {
-    gdim[1] = (cuuint64_t)d.B; gdim[2] = (cuuint64_t)d.T;
-    gstr[0] = (cuuint64_t)a.xsb * esz; gstr[1] = (cuuint64_t)a.xst * esz;
-    box[1] = TC_CONV_ROWS; box[2] = 1;
-  } else {
-    gdim[1] = (cuuint64_t)d.T; gdim[2] = (cuuint64_t)d.B;
-    gstr[0] = (cuuint64_t)a.xst * esz; gstr[1] = (cuuint64_t)a.xsb * esz;
-    box[1] = 1; box[2] = TC_CONV_ROWS;
-  }
-  const CUresult cr = encode(&map, d.x_dtype == FGRNN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                             const_cast<void*>(a.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) { set_error_detail("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return FGRNN_ERR_CUDA; }
+  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, TC_CONV_ROWS, &ta.x_time_outer);
+  if (rc) return rc;
   const TcSmemLayout L = tc_smem_layout(d.I, ta.KI, esz);
   FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const unsigned grid = (unsigned)((d.B + TC_ROWS - 1) / TC_ROWS);

@@ -274,4 +274,303 @@ int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream) {
   return FGRNN_OK;
 }
 
+// =============================================================================================
+// tc_bwd_rec_kernel -- the serial part of BPTT (cuda/fastgrnn_cuda_kernel.cu:109-118, 537) as a persistent
+// reverse kernel on the tensor cores, the mirror image of fgrnn_tc.cu:
+//     G = g_t + delta;   dc = (sz (1 - z) + sn)(1 - c^2) G;   dz = (h_{t-1} - sz c) z (1 - z) G;   dpre = dc + dz
+//     delta <- z G + dpre . U^T            (after t = 0: delta = d h0)
+//   A operand = U (bf16 hi/lo) resident in tensor memory, lane = k (the unit of delta), column pair = n
+//   B operand = dpre_t tile (bf16 hi/lo, MN-major) written by the epilogue warps, N = 32 rows per sub-tile
+//   D         = CA | CB | M1 | M2 fp32 accumulators per sub-tile, 8 MMAs from each of three issuing warps
+// One CTA = 64 batch rows = two sub-tiles owned by 8 epilogue warps each (thread = unit, 16 rows), one producer
+// warp streams grad_h / z / c / h_{t-1} tiles into a 3-stage shared-memory ring with TMA
+// (one 16 KB TMA box per array, 3-D maps over the caller's strides).  The bias / zeta / nu sums
+// live in per-thread registers for the whole kernel and leave as one partial row per CTA.
+// =============================================================================================
+constexpr int BR_H = 128, BR_NS = 32, BR_NT = 2, BR_ROWS = BR_NS * BR_NT;
+constexpr int BR_EPI_WARPS = 16, BR_MMA_WARPS = 3;
+constexpr int BR_W_PROD = BR_EPI_WARPS, BR_W_MMA = BR_EPI_WARPS + 1;
+constexpr int BR_THREADS = 32 * (BR_EPI_WARPS + 1 + BR_MMA_WARPS);      // 640
+constexpr int BR_STAGES = 3;
+constexpr int BR_ARR = BR_NS * BR_H * 4;                                // one [32][128] fp32 tile
+constexpr int BR_STAGE = 4 * BR_ARR;                                    // g | z | c | h_{t-1}
+constexpr int BR_OPT = BR_NS * BR_H * 2;                                // one bf16 operand tile
+constexpr int BR_TM_U_HI = 0, BR_TM_U_LO = 64, BR_TM_ACC = 128, BR_TM_ACC_PER_TILE = 4 * BR_NS;
+constexpr uint32_t BR_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BR_NS >> 3) << 17) | ((uint32_t)(BR_H >> 4) << 24);
+constexpr uint32_t BR_KSTEP = (2 * (BR_NS >> 3) * 128) >> 4;
+
+struct BrSmem { int stage, op, bars, red, total; };
+__host__ __device__ inline BrSmem br_smem_layout() {
+  BrSmem L;
+  L.stage = 0;
+  L.op = BR_STAGES * BR_STAGE;                  // [NT][hi|lo][BR_OPT]
+  L.bars = L.op + BR_NT * 2 * BR_OPT;
+  L.red = L.bars + 16 * 8;                      // 32 floats of reduction scratch
+  L.total = L.red + 32 * 4;
+  return L;
+}
+
+struct BrMaps { CUtensorMap g, z, c, hs, h0; };
+
+__global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwdArgs a, const __grid_constant__ BrMaps maps, const int g_time_outer, const int hs_time_outer) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const BrSmem L = br_smem_layout();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  __shared__ uint32_t tmem_base_s;
+  const Dims d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * BR_ROWS;
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  const int B_HREADY = 0, B_DFULL = 2, B_SFULL = 4, B_SEMPTY = 7;      // operand ready | accumulators ready | ring
+
+  if (warp == BR_W_MMA) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (tid == 0) {
+    for (int s = 0; s < BR_NT; ++s) { mbar_init(bar(B_HREADY + s), BR_EPI_WARPS / BR_NT); mbar_init(bar(B_DFULL + s), BR_MMA_WARPS); }
+    for (int st = 0; st < BR_STAGES; ++st) { mbar_init(bar(B_SFULL + st), 1); mbar_init(bar(B_SEMPTY + st), BR_EPI_WARPS / BR_NT); }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tmem_base_s != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
+  const bool hp_zero_at_t0 = a.h0 == nullptr;
+
+  if (warp >= BR_W_MMA) {
+    // =========================== MMA issuers ======================================================
+    const int role = warp - BR_W_MMA;
+    const bool leader = elect_one();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint64_t dD0 = make_desc_mn(smem_u32(sm + L.op), BR_NS);
+    for (int it = 0; it < d.T; ++it) {
+#pragma unroll
+      for (int s = 0; s < BR_NT; ++s) {
+        const uint64_t dhi = dD0 + (uint64_t)(s * ((2 * BR_OPT) >> 4)), dlo = dhi + (BR_OPT >> 4);
+        const uint32_t acc = tmem + BR_TM_ACC + s * BR_TM_ACC_PER_TILE;
+        mbar_wait(bar(B_HREADY + s), it & 1);          // dpre_t operand tile written, accumulators drained
+        tc_fence_after();
+        if (leader) {
+          if (role == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ts1(acc, tmem + BR_TM_U_LO + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
+              umma_ts1(acc, tmem + BR_TM_U_HI + ks * 8, dlo + ks * BR_KSTEP, BR_IDESC, 1);
+            }
+          } else if (role == 1) {
+#pragma unroll
+            for (int ks = 4; ks < 8; ++ks) {
+              umma_ts1(acc + BR_NS, tmem + BR_TM_U_LO + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 4);
+              umma_ts1(acc + BR_NS, tmem + BR_TM_U_HI + ks * 8, dlo + ks * BR_KSTEP, BR_IDESC, 1);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ts1(acc + 2 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
+#pragma unroll
+            for (int ks = 4; ks < 8; ++ks) umma_ts1(acc + 3 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 4);
+          }
+          umma_commit1(bar(B_DFULL + s));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == BR_W_PROD) {
+    // =========================== producer: one TMA box per array per sub-tile step ==================
+    // grad_h and the hidden states by the caller's strides, z_s / c_s [T][B][H]; rows past the batch end are
+    // zero-filled by the TMA unit, so the epilogue needs no masking of its sums.
+    tc_fence_before();
+    __syncthreads();
+    if (lane == 0) {
+      for (int it = 0; it < d.T; ++it) {
+        const int t = d.T - 1 - it;
+        for (int s = 0; s < BR_NT; ++s) {
+          const int q = it * BR_NT + s, st = q % BR_STAGES;
+          const int first = row0 + s * BR_NS;
+          const bool with_hp = !(t == 0 && hp_zero_at_t0);
+          if (q >= BR_STAGES) mbar_wait(bar(B_SEMPTY + st), ((q / BR_STAGES) - 1) & 1);
+          const uint32_t fb = bar(B_SFULL + st), dst = smem_u32(sm + L.stage + st * BR_STAGE);
+          mbar_expect_tx(fb, (uint32_t)BR_ARR * (with_hp ? 4u : 3u));
+          if (g_time_outer) tma_load_3d(dst, &maps.g, 0, first, t, fb); else tma_load_3d(dst, &maps.g, 0, t, first, fb);
+          tma_load_3d(dst + BR_ARR, &maps.z, 0, first, t, fb);
+          tma_load_3d(dst + 2 * BR_ARR, &maps.c, 0, first, t, fb);
+          if (t > 0) {
+            if (hs_time_outer) tma_load_3d(dst + 3 * BR_ARR, &maps.hs, 0, first, t - 1, fb); else tma_load_3d(dst + 3 * BR_ARR, &maps.hs, 0, t - 1, first, fb);
+          } else if (with_hp) {
+            tma_load_3d(dst + 3 * BR_ARR, &maps.h0, 0, first, 0, fb);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue warps ===================================================
+    const int ew = warp, quad = warp & 3, es = (ew >> 2) & 1, rh = ew >> 3;
+    const int n = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // U -> tensor memory: A[m = k][kk = n] = U_canonical[k][n]; this thread's row m = n (lane), the four warps of
+    // a quadrant take 32 columns each
+    {
+      const int part = ew >> 2;
+      const bool hi_layout = a.layout == FGRNN_LAYOUT_HI;
+      float uv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int kk = part * 32 + j;
+        uv[j] = hi_layout ? __ldg(a.U + (size_t)kk * BR_H + n) : __ldg(a.U + (size_t)n * BR_H + kk);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split2_bf16(uv[c * 16 + 2 * j], uv[c * 16 + 2 * j + 1], hi[j], lo[j]);
+        tmem_st8(tmem + lane_base + BR_TM_U_HI + part * 16 + c * 8, hi);
+        tmem_st8(tmem + lane_base + BR_TM_U_LO + part * 16 + c * 8, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
+    const float2 sz2 = make_float2(sz, sz), sn2 = make_float2(sn, sn), msz2 = make_float2(-sz, -sz), one2 = make_float2(1.f, 1.f);
+    const int first_row = row0 + es * BR_NS + rh * 16;
+    const int rows_left = d.B - first_row;
+    unsigned char* hop = sm + L.op + es * (2 * BR_OPT) + (n >> 3) * ((BR_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
+    const uint32_t acc = tmem + lane_base + BR_TM_ACC + es * BR_TM_ACC_PER_TILE + rh * 16;
+    float* dpre_p = a.dpre_ws + (size_t)first_row * BR_H + n;             // + t*B*H per step
+    float2 carry[8];                                                       // z G of the previous (later) step
+#pragma unroll
+    for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
+    float2 db_u = make_float2(0.f, 0.f), db_g = db_u, dze = db_u, dnu = db_u;
+
+    for (int it = 0; it <= d.T; ++it) {
+      const int t = d.T - 1 - it;
+      float2 G[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) G[q] = carry[q];
+      if (it > 0) {                                     // delta += dpre_{t+1} . U^T
+        mbar_wait(bar(B_DFULL + es), (it - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float va[8], vb[8], v1[8], v2[8];
+          tmem_ld8(acc + g * 8, va);
+          tmem_ld8(acc + BR_NS + g * 8, vb);
+          tmem_ld8(acc + 2 * BR_NS + g * 8, v1);
+          tmem_ld8(acc + 3 * BR_NS + g * 8, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
+            const float2 mm = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
+            G[g * 4 + q] = __fadd2_rn(G[g * 4 + q], mm);
+          }
+        }
+      }
+      if (it == d.T) {                                  // delta after t = 0 is d h0
+        if (a.d_h0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < rows_left) a.d_h0[(size_t)(first_row + j) * BR_H + n] = (j & 1) ? G[j >> 1].y : G[j >> 1].x;
+        }
+        break;
+      }
+      const int qi = it * BR_NT + es, st = qi % BR_STAGES;
+      mbar_wait_poll(bar(B_SFULL + st), (qi / BR_STAGES) & 1);
+      const float* tile = reinterpret_cast<const float*>(sm + L.stage + st * BR_STAGE) + (rh * 16) * BR_H + n;
+      const bool hp_zero = t == 0 && hp_zero_at_t0;
+      uint32_t hi[8], lo[8];
+      float2 dp[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float* e0 = tile + (2 * q) * BR_H;
+        const float2 g = make_float2(e0[0], e0[BR_H]);
+        const float2 z = make_float2(e0[BR_ARR / 4], e0[BR_ARR / 4 + BR_H]);
+        const float2 c = make_float2(e0[2 * (BR_ARR / 4)], e0[2 * (BR_ARR / 4) + BR_H]);
+        const float2 hp = hp_zero ? make_float2(0.f, 0.f) : make_float2(e0[3 * (BR_ARR / 4)], e0[3 * (BR_ARR / 4) + BR_H]);
+        const float2 Gq = __fadd2_rn(G[q], g);
+        const float2 w = __fadd2_rn(one2, make_float2(-z.x, -z.y));                       // 1 - z
+        const float2 cG = __fmul2_rn(c, Gq);
+        const float2 u = __ffma2_rn(make_float2(-c.x, -c.y), c, one2);                     // 1 - c^2
+        const float2 dc = __fmul2_rn(__fmul2_rn(__ffma2_rn(sz2, w, sn2), u), Gq);          // cu:112
+        const float2 zw = __fmul2_rn(z, w);                                                // sigmoid'(.) on the output
+        const float2 dz = __fmul2_rn(__fmul2_rn(__ffma2_rn(msz2, c, hp), zw), Gq);         // cu:113
+        dp[q] = __fadd2_rn(dc, dz);
+        carry[q] = __fmul2_rn(z, Gq);                                                      // cu:110 d_old_h = z g
+        db_u = __fadd2_rn(db_u, dc); db_g = __fadd2_rn(db_g, dz);
+        dze = __ffma2_rn(w, cG, dze);                                                      // cu:116 (sigmoid' applied at the end)
+        dnu = __fadd2_rn(dnu, cG);                                                         // cu:117
+        split2_bf16(dp[q].x, dp[q].y, hi[q], lo[q]);
+      }
+      *reinterpret_cast<uint4*>(hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(hop + BR_OPT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(hop + BR_OPT + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(B_HREADY + es)); mbar_arrive(bar(B_SEMPTY + st)); }
+      float* dst = dpre_p + (size_t)t * d.B * BR_H;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (2 * q < rows_left) dst[(2 * q) * BR_H] = dp[q].x;
+        if (2 * q + 1 < rows_left) dst[(2 * q + 1) * BR_H] = dp[q].y;
+      }
+    }
+
+    // per-CTA partial row: d_bias_gate | d_bias_update | d_zeta (raw) | d_nu (raw); fixed summation order
+    asm volatile("bar.sync 1, %0;" ::"n"(BR_EPI_WARPS * 32) : "memory");   // the ring is free: reuse it as scratch
+    float* scr = reinterpret_cast<float*>(sm + L.stage);                    // [4 contributors][2][128] | [16 warps][2]
+    const int contrib = es * 2 + rh;
+    scr[(contrib * 2 + 0) * BR_H + n] = db_g.x + db_g.y;
+    scr[(contrib * 2 + 1) * BR_H + n] = db_u.x + db_u.y;
+    float vz = dze.x + dze.y, vn = dnu.x + dnu.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { vz += __shfl_xor_sync(0xffffffffu, vz, o); vn += __shfl_xor_sync(0xffffffffu, vn, o); }
+    if (lane == 0) { scr[8 * BR_H + ew * 2] = vz; scr[8 * BR_H + ew * 2 + 1] = vn; }
+    asm volatile("bar.sync 1, %0;" ::"n"(BR_EPI_WARPS * 32) : "memory");
+    float* outp = a.rec_partial + (size_t)blockIdx.x * (2 * BR_H + 2);
+    if (ew < 8) {                                        // 256 threads: one bias entry each
+      const int which = ew >> 2, nn = (ew & 3) * 32 + lane;
+      float s = 0.f;
+#pragma unroll
+      for (int cidx = 0; cidx < 4; ++cidx) s += scr[(cidx * 2 + which) * BR_H + nn];
+      outp[which * BR_H + nn] = s;
+    } else if (ew == 8 && lane < 2) {
+      float s = 0.f;
+      for (int w = 0; w < BR_EPI_WARPS; ++w) s += scr[8 * BR_H + w * 2 + lane];
+      outp[2 * BR_H + lane] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == BR_W_MMA) tmem_dealloc(tmem, 512);
+}
+
+bool tc_bwd_rec_supports(const Dims& d) {
+  return d.rW == 0 && d.rU == 0 && d.H == BR_H && d.gate_nl == FGRNN_NL_SIGMOID && d.update_nl == FGRNN_NL_TANH;
+}
+int tc_bwd_rec_ctas(const Dims& d) { return (d.B + BR_ROWS - 1) / BR_ROWS; }
+
+int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream) {
+  const Dims& d = a.d;
+  if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
+  BrMaps maps;
+  int g_to = 0, hs_to = 0, dummy = 0, rc;
+  if ((rc = make_row_tile_map(&maps.g, a.grad_h, false, BR_H, d.B, d.T, a.gsb, a.gst, BR_NS, &g_to))) return rc;
+  if ((rc = make_row_tile_map(&maps.z, a.z_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  if ((rc = make_row_tile_map(&maps.c, a.c_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  // T == 1 never reads the hidden states (h_{t-1} is h0): any valid pointer keeps the descriptor well formed
+  const float* hs = a.hs ? a.hs : a.z_s;
+  if ((rc = make_row_tile_map(&maps.hs, hs, false, BR_H, d.B, d.T, a.hs ? a.hsb : BR_H, a.hs ? a.hst : (int64_t)d.B * BR_H, BR_NS, &hs_to))) return rc;
+  const float* h0 = a.h0 ? a.h0 : a.z_s;
+  if ((rc = make_row_tile_map(&maps.h0, h0, false, BR_H, d.B, 1, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  const BrSmem L = br_smem_layout();
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_bwd_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  tc_bwd_rec_kernel<<<tc_bwd_rec_ctas(d), BR_THREADS, L.total, stream>>>(a, maps, g_to, hs_to);
+  FGRNN_LAUNCH_CHECK("tc_bwd_rec_kernel");
+  return FGRNN_OK;
+}
+
 }  // namespace fgrnn

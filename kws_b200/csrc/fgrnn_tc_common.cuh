@@ -30,6 +30,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spins > (1u << 20)) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
   }
 }
+// Polling wait (no suspend hint) for barriers completed by bulk-copy transaction counts on the critical path
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -130,6 +139,50 @@ __device__ __forceinline__ void umma_ss1(uint32_t d_tmem, uint64_t a_desc, uint6
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+
+// ---- host side: TMA tensor maps -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Map over a [rows][steps][inner] tensor given by element strides (inner contiguous): box = `box_rows` rows of one
+// step.  The two outer dimensions are ordered by stride; *time_outer tells the kernel the coordinate order:
+// 0 -> {0, t, row}, 1 -> {0, row, t}.  Rows past the end are zero-filled by the TMA unit.
+static inline int make_row_tile_map(CUtensorMap* map, const void* base, bool bf16, int inner, int rows, int steps,
+                                    int64_t row_stride, int64_t step_stride, int box_rows, int* time_outer) {
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) { set_error_detail("cuTensorMapEncodeTiled is not available from the driver"); return FGRNN_ERR_CUDA; }
+  const int esz = bf16 ? 2 : 4;
+  *time_outer = step_stride >= row_stride ? 1 : 0;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  gdim[0] = (cuuint64_t)inner; box[0] = (cuuint32_t)inner;
+  if (*time_outer) {
+    gdim[1] = (cuuint64_t)rows; gdim[2] = (cuuint64_t)steps;
+    gstr[0] = (cuuint64_t)row_stride * esz; gstr[1] = (cuuint64_t)step_stride * esz;
+    box[1] = (cuuint32_t)box_rows; box[2] = 1;
+  } else {
+    gdim[1] = (cuuint64_t)steps; gdim[2] = (cuuint64_t)rows;
+    gstr[0] = (cuuint64_t)step_stride * esz; gstr[1] = (cuuint64_t)row_stride * esz;
+    box[1] = 1; box[2] = (cuuint32_t)box_rows;
+  }
+  const CUresult cr = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
+                             gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error_detail("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return FGRNN_ERR_CUDA; }
+  return FGRNN_OK;
 }
 
 }  // namespace fgrnn
