@@ -48,6 +48,9 @@ constexpr int TC_MAX_KI = 64;                  // input features padded to a mul
 constexpr int TM_U_HI = 0, TM_U_LO = 64, TM_W_HI = 128, TM_W_LO = 160, TM_ACC = 192;
 constexpr int TM_ACC_PER_TILE = 4 * TC_NS;     // CA | CB | M1 | M2
 constexpr int TC_TMEM_COLS = 512;
+#ifndef TC_CRIT_WAIT
+#define TC_CRIT_WAIT mbar_wait      // waits on the step-critical path (mbar_wait_poll = spin without suspend hint)
+#endif
 #ifndef TC_STAGGER_NS
 #define TC_STAGGER_NS 500
 #endif
@@ -179,7 +182,9 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
   const uint32_t row_bytes = cx.out_row * 4u;
   for (int t = 0; t < cx.T; ++t) {
     if (cx.trace) TC_TRACE(t, cx.s, 0);
-    mbar_wait(cx.bar_dfull, t & 1);
+#ifndef TC_EXP_NO_DWAIT
+    TC_CRIT_WAIT(cx.bar_dfull, t & 1);
+#endif
     tc_fence_after();
     if (cx.trace) TC_TRACE(t, cx.s, 1);
     uint32_t hi[8], lo[8];
@@ -197,7 +202,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
         const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
         const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
         float2 z, c;
+#ifdef TC_EXP_NO_MATH
+        hst[g * 4 + q] = tot; z = tot; c = tot;
+#else
         hst[g * 4 + q] = gate_update2(tot, hst[g * 4 + q], kc, z, c);
+#endif
         split_pair(hst[g * 4 + q], hi[g * 4 + q], lo[g * 4 + q]);
         if (SAVE) {                                      // training forward: z_s, c_s (cu:340-341)
           const int rj = g * 8 + 2 * q;
@@ -219,12 +228,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
     if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready);
     if (cx.trace) TC_TRACE(t, cx.s, 4);
     if (HAS_OUT) {
-      char* pr = outp;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(pr) = hst[q].x;
-        if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(pr + row_bytes) = hst[q].y;
-        pr += 2 * (size_t)row_bytes;
+        if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
+        if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
       }
       outp += (size_t)cx.out_step * 4u;
     }
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         const uint64_t dHhi = dH0 + (uint64_t)(s * htile_step), dHlo = dHhi + hlo_step;
         const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
         if (role == 0) TC_TRACE(t, s, 8);
-        mbar_wait(bar(B_HREADY + s), t & 1);           // h_{t-1} operand tile written, D of step t-1 drained
+        TC_CRIT_WAIT(bar(B_HREADY + s), t & 1);        // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
         if (role == 0) TC_TRACE(t, s, 9);
         if (leader) {
