@@ -166,3 +166,32 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.FastGRNNLibraryError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_plan_selection_between_kernel_families(lib):
+    """fgrnn_*_plan is pure host logic: the tcgen05 family takes the flagship shape, everything it does not
+    cover falls through to the FFMA / generic families; forcing an unsupported family is an error, not a fallback."""
+    plan = lambda **kw: lib.fgrnn_forward_plan(C.byref(_fwd(**kw)))
+    assert plan() == _lib.PATH_TCGEN05                                       # full rank, H=128, I=32, aligned
+    assert plan(I=64, x_stride_b=192, x_stride_t=64) == _lib.PATH_TCGEN05
+    assert plan(x_dtype=_lib.BF16, x=0x1000) == _lib.PATH_TCGEN05
+    assert plan(I=28, x_stride_b=84, x_stride_t=28) == _lib.PATH_SMEM        # I % 8 != 0: FFMA family
+    assert plan(x=0x1004) == _lib.PATH_GENERIC                               # x not 16-byte aligned: no vector / TMA access
+    assert plan(gate_nl=2) == _lib.PATH_SMEM                                 # tanh gate: not in the tensor-core epilogue
+    assert plan(H=256, out_stride_b=768, out_stride_t=256) == _lib.PATH_GENERIC
+    assert plan(rU=32, U1=0x1000, U2=0x1000) == _lib.PATH_GENERIC            # low rank
+    assert plan(force_path=_lib.PATH_SMEM) == _lib.PATH_SMEM
+    d = _fwd(I=28, x_stride_b=84, x_stride_t=28, force_path=_lib.PATH_TCGEN05)
+    assert lib.fgrnn_forward(C.byref(d), None) == _lib.ERR_SHAPE and lib.fgrnn_forward_plan(C.byref(d)) == -1
+
+    g = _lib.FgrnnBackward()
+    C.memmove(C.byref(g.p), C.byref(_fwd().p), C.sizeof(_lib.FgrnnProblem))
+    g.grad_h = g.hs = g.z_s = g.c_s = 0x1000
+    g.grad_stride_b, g.grad_stride_t, g.hs_stride_b, g.hs_stride_t = 384, 128, 384, 128
+    g.d_W = g.d_U = 0x1000
+    assert lib.fgrnn_backward_plan(C.byref(g)) == _lib.PATH_TCGEN05
+    g.grad_stride_b = 386                                                    # rows no longer 16-byte aligned
+    assert lib.fgrnn_backward_plan(C.byref(g)) == _lib.PATH_GENERIC
+    g.grad_stride_b = 384
+    g.p.gate_nl = 2
+    assert lib.fgrnn_backward_plan(C.byref(g)) == _lib.PATH_SMEM
