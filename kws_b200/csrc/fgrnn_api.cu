@@ -73,10 +73,10 @@ struct DeviceGuard {
   bool ok = false;
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) return;
-    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) return;
-    // bind the primary context to this thread: the driver-API tensor-map encoder (cuTensorMapEncodeTiled) returns
-    // CUDA_ERROR_INVALID_CONTEXT on threads that never touched the runtime (autograd worker threads)
-    if (cudaFree(nullptr) != cudaSuccess) return;
+    // cudaSetDevice even when the ordinal is already current: it binds the primary context to THIS thread, which the
+    // driver-API tensor-map encoder (cuTensorMapEncodeTiled) needs -- autograd worker threads that never touched
+    // the runtime otherwise get CUDA_ERROR_INVALID_CONTEXT.  (Legal during stream capture, unlike cudaFree(0).)
+    if (cudaSetDevice(dev) != cudaSuccess) return;
     ok = true;
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }

@@ -32,6 +32,15 @@
 
 namespace fgrnn {
 
+#ifdef TC_EXP_SCALAR_MATH      // experiment: scalar FFMA/FADD/FMUL instead of the packed fp32x2 instructions
+__device__ __forceinline__ float2 s_ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 s_fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 s_fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#define __ffma2_rn s_ffma2
+#define __fadd2_rn s_fadd2
+#define __fmul2_rn s_fmul2
+#endif
+
 constexpr int TC_H = 128;                      // hidden size = UMMA M
 constexpr int TC_NS = 32;                      // batch rows per sub-tile = UMMA N
 constexpr int TC_NT = 2;                       // sub-tiles per CTA
@@ -131,7 +140,11 @@ __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiCo
   tot.x = fmaxf(tot.x, k.tmin); tot.y = fmaxf(tot.y, k.tmin);
   const float2 ag = __ffma2_rn(tot, k.kS, k.cg);               // -(pre + b_g) * log2(e)
   float2 eg, eu;
+#ifdef TC_EXP_NO_MUFU
+  eg = __fmul2_rn(ag, ag);
+#else
   eg.x = ex2_approx(ag.x); eg.y = ex2_approx(ag.y);
+#endif
 #if FGRNN_TC_ONE_EX2
   eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                   // cu = exp(2 (b_g - b_u))
 #else
@@ -142,7 +155,11 @@ __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiCo
   const float2 a = __fadd2_rn(eg, one), b = __fadd2_rn(eu, one);
   const float2 ab = __fmul2_rn(a, b);
   float2 r;
+#ifdef TC_EXP_NO_MUFU
+  r = __fmul2_rn(ab, ab);
+#else
   r.x = rcp_approx(ab.x); r.y = rcp_approx(ab.y);
+#endif
   z = __fmul2_rn(r, b);                                        // rnn.py:290
 #if FGRNN_TC_C_FORM
   c = __fmul2_rn(__fadd2_rn(make_float2(-eu.x, -eu.y), one), __fmul2_rn(r, a));            // (1 - e_u) / (1 + e_u)
@@ -154,6 +171,9 @@ __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiCo
 
 // h (two rows) -> fp16 hi pair and fp16 lo pair (residual, exact subtraction); |h| < 65504
 __device__ __forceinline__ void split_pair(float2 h, uint32_t& hi, uint32_t& lo) {
+#ifdef TC_EXP_NO_SPLIT
+  hi = __float_as_uint(h.x); lo = __float_as_uint(h.y); return;
+#endif
   const __half2 hh = __float22half2_rn(h);
   const float2 hf = __half22float2(hh);
   const __half2 hl = __float22half2_rn(__fadd2_rn(h, make_float2(-hf.x, -hf.y)));
@@ -349,6 +369,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         const uint64_t dHhi = dH0 + (uint64_t)(s * htile_step), dHlo = dHhi + hlo_step;
         const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
         if (role == 0) TC_TRACE(t, s, 8);
+#ifdef TC_EXP_KEEPWARM
+        if (role == 1) {       // experiment: keep the tensor pipe awake with dummy MMAs into spare TMEM columns while waiting
+          while (!mbar_test(bar(B_HREADY + s), t & 1)) {
+            if (leader) umma_ts1(tmem + 448, tmem + TM_W_HI, dX0, TC_IDESC_X, 0);
+            __syncwarp();
+            __nanosleep(TC_EXP_KEEPWARM);
+          }
+        }
+#endif
         TC_CRIT_WAIT(bar(B_HREADY + s), t & 1);        // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
         if (role == 0) TC_TRACE(t, s, 9);

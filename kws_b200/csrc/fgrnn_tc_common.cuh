@@ -30,6 +30,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spins > (1u << 20)) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
   }
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Polling wait (no suspend hint) for barriers completed by bulk-copy transaction counts on the critical path
 __device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;

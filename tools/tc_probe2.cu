@@ -35,6 +35,9 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 __device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -124,6 +127,31 @@ __global__ void __launch_bounds__(128, 1) ts_kernel(const __half* A, const __hal
       t1 = clock64();
     }
   }
+  if (mode == 3) {
+    // bursts of n_mma MMAs separated by an idle gap of `nacc` cycles: issue+complete time of each burst
+    if (warp == 0) {
+      for (int rep = 0; rep < 6; ++rep) {
+        const long long b0 = clock64();
+#pragma unroll 1
+        for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) umma_ts_elect(tmem + (uint32_t)((j & 3) * 32), tmem + A_COL + j * 8, dB + j * kstep, idesc, 1);
+        }
+        const long long b1 = clock64();
+        umma_commit_elect(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), rep & 1);
+        const long long b2 = clock64();
+        if (lane == 0) { tout[2 * rep] = b1 - b0; tout[2 * rep + 1] = b2 - b0; }
+        while (clock64() - b2 < nacc) { }
+      }
+    }
+    __syncthreads();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    return;
+  }
   mbar_wait(smem_u32(&bar), 0);
   tc_fence_after();
   if (tid == 0 && mode != 0) { tout[0] = clock64() - t0; tout[1] = t1 - t0; }
@@ -149,7 +177,7 @@ int main() {
     for (auto& v : A) v = __float2half((float)(rand() % 2001 - 1000) / 1000.f);
     for (auto& v : B) v = __float2half((float)(rand() % 2001 - 1000) / 1000.f);
     __half *dA, *dB; float* dD; long long* dT;
-    CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dT, 32));
+    CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dT, 128));
     CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
     const size_t smem = 64 * 1024;
     CK(cudaFuncSetAttribute(ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -171,6 +199,16 @@ int main() {
         CK(cudaMemcpy(h, dT, 16, cudaMemcpyDeviceToHost));
         printf("TS-TIME N=%3d accumulators=%d n_mma=%3d : total %6lld cyc (%.1f/mma)  issue %6lld cyc (%.1f/mma)\n", N, nacc, n_mma, h[0], (double)h[0] / n_mma, h[1], (double)h[1] / n_mma);
       }
+    if (N == 32) {
+      for (int gap : {0, 200, 500, 1000, 2000, 5000}) {
+        long long h[12];
+        ts_kernel<<<1, 128, smem>>>(dA, dB, dD, dT, K, N, 3, 32, gap); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, dT, 96, cudaMemcpyDeviceToHost));
+        printf("TS-GAP N=32 burst=32 idle gap %5d cyc : issue/complete per burst:", gap);
+        for (int r = 0; r < 6; ++r) printf(" %lld/%lld", h[2 * r], h[2 * r + 1]);
+        printf("\n");
+      }
+    }
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dT);
   }
   return 0;
