@@ -369,15 +369,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         const uint64_t dHhi = dH0 + (uint64_t)(s * htile_step), dHlo = dHhi + hlo_step;
         const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
         if (role == 0) TC_TRACE(t, s, 8);
-#ifdef TC_EXP_KEEPWARM
-        if (role == 1) {       // experiment: keep the tensor pipe awake with dummy MMAs into spare TMEM columns while waiting
-          while (!mbar_test(bar(B_HREADY + s), t & 1)) {
-            if (leader) umma_ts1(tmem + 448, tmem + TM_W_HI, dX0, TC_IDESC_X, 0);
-            __syncwarp();
-            __nanosleep(TC_EXP_KEEPWARM);
-          }
-        }
-#endif
         TC_CRIT_WAIT(bar(B_HREADY + s), t & 1);        // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
         if (role == 0) TC_TRACE(t, s, 9);
