@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "smem", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="training workloads: time the eager step, not the CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -258,23 +259,34 @@ def main():
             bucket.all_reduce_mean()
         opt.step()
 
+    graphed = False
+    run_step = step
+    if train and not args.no_graph:
+        try:                                      # the whole step as one CUDA graph (kws_b200/graphs.py)
+            from kws_b200 import graphs
+            cap = graphs.CapturedStep(step, warmup=args.warmup)
+            run_step, graphed = cap, True
+        except Exception as e:                    # noqa: BLE001 -- report and time the eager step instead
+            print("bench.py: CUDA-graph capture failed (%s); timing the eager step" % (e,), file=sys.stderr)
+            run_step = step
+
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(device)
 
     for _ in range(args.warmup):
-        step()
+        run_step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
     for i in range(args.steps):
-        step()
+        run_step()
         evs[i + 1].record()
     barrier()
-    launches = _lib.launch_count() - launches0
+    launches = cap.launches * args.steps if graphed else _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
@@ -355,7 +367,7 @@ def main():
             "config": {"workload": w["desc"], "name": args.workload, "per_gpu_batch": B, "global_batch": B * world,
                        "T": T, "input": I, "hidden": H, "wRank": w["wR"], "uRank": w["uR"], "x_dtype": w["x"],
                        "layout": "(B,T,F) contiguous" if not train else "(T,B,F) contiguous",
-                       "weight_layout": args.layout, "kernel_path": plan,
+                       "weight_layout": args.layout, "kernel_path": plan, "cuda_graph": graphed,
                        "l2": "inputs+outputs per step = %.0f MB > 126 MB L2, no flush needed"
                              % ((algorithmic_bytes_per_seq(w) * B) / 1e6),
                        "parallelism": "batch-sharded x%d%s" % (world, ", NCCL grad all-reduce" if train else ", no collective")},
