@@ -162,3 +162,23 @@ def test_training_step_replays_from_a_cuda_graph():
     torch.cuda.synchronize()
     for a, b in zip(plist_e, plist_g):       # 3 eager warm-ups + 2 replays == 5 eager steps, bit for bit
         assert torch.equal(a, b)
+
+
+def test_tcgen05_last_state_only_and_chunked_carry():
+    """want_states=False writes no [B,T,H] tensor at all; feeding h_T of one chunk as h0 of the next is
+    bit-identical to one long call (the state never leaves fp32)."""
+    from kws_b200 import _lib, engine
+    torch.manual_seed(21)
+    p = O.init_params(32, 128)
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    x = torch.randn(100, 30, 32, device=dev())
+    kw = dict(layout="IH", batch_first=True, force_path=_lib.PATH_TCGEN05)
+    full, _, _, last = engine.forward(x, params, None, want_last=True, **kw)
+    none_out, _, _, last2 = engine.forward(x, params, None, want_states=False, **kw)
+    assert none_out is None and torch.equal(last, last2)
+    a, _, _, ha = engine.forward(x[:, :11].contiguous(), params, None, want_last=True, **kw)
+    b, _, _, hb = engine.forward(x[:, 11:].contiguous(), params, ha, want_last=True, **kw)
+    assert torch.equal(torch.cat([a, b], 1), full) and torch.equal(hb, last)
+    # a strided (non-contiguous) time slice goes through the TMA map without a copy
+    c, _, _, _ = engine.forward(x[:, 11:], params, ha, **kw)
+    assert torch.equal(c, b)
