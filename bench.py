@@ -72,21 +72,68 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: an NVML polling thread (a sample
+    every ~0.5 ms, so even a 3 ms region is covered); `nvidia-smi -lms` is the fallback when NVML is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
+        import threading
         self.proc = None
+        self.samples = []            # (sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        except Exception:                         # noqa: BLE001 -- no NVML binding: fall back to nvidia-smi
+            self._nvml = None
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
+
+    def _poll(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    power = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                except Exception:                 # noqa: BLE001
+                    power = 0.0
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:                 # noqa: BLE001 -- older bindings
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.samples.append((mhz, power, reasons))
+            except Exception:                     # noqa: BLE001
+                pass
+            time.sleep(0.0005)
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            mask = 0
+            for _, _, r in self.samples:
+                mask |= r
+            reasons = sorted(name for bit, name in self.REASON_BITS.items() if mask & bit)
+            return {"sm_mhz": statistics.median(m for m, _, _ in self.samples), "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "power_w_max": max(p for _, p, _ in self.samples),
+                    "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -112,7 +159,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+                "power_w_max": max(power), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_params(w, device, layout="IH"):
@@ -185,7 +232,7 @@ def run_reference(args, w, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
