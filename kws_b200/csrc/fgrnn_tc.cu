@@ -4,7 +4,7 @@
 //   A operand = the weights, resident in TENSOR MEMORY for the whole kernel (lane = hidden unit n,
 //               32-bit column c = fp16 pair k = 2c, 2c+1);  M = H = 128 is always a full-rate UMMA M
 //   B operand = the streamed data in shared memory: x_t tile (K-major) and h_{t-1} tile (MN-major),
-//               N = 32 batch rows per sub-tile
+//               N = 32 batch rows per sub-tile (a tcgen05.mma with A in TMEM costs ~18 cycles for any N <= 32)
 //   D         = fp32 accumulators in tensor memory, lane = hidden unit, column = batch row
 //
 // fp32 parity on fp16 tensor cores (measured and modelled in tools/tc_probe.cu, tools/fit_mma_model.py,
@@ -14,19 +14,22 @@
 //   * one tcgen05.mma aligns its 16 products and the accumulator to the largest exponent, TRUNCATES every
 //     addend at 2^(emax-25) and truncates the sum to fp32 -- a toward-zero bias per MMA.  A single chain of
 //     30 MMAs lands at 1.5-1.9x the (rtol 1e-5, atol 1e-6) budget.  So the small lo terms accumulate in
-//     their own accumulator C (their truncation error is 2^-11 smaller) and the hi.hi terms are split over
-//     two short chains M1, M2; the epilogue adds the three in fp32 round-to-nearest:  0.54-0.62 of the
-//     budget against the oracle, the same as the FFMA kernel.
+//     their own accumulators CA, CB (their truncation error is 2^-11 smaller) and the hi.hi terms are split over
+//     two short chains M1, M2; the epilogue adds the four in fp32 round-to-nearest:  0.54-0.62 of the
+//     budget against the oracle in emulation, 0.57-0.79 measured, the same class as the FFMA kernel.
 //
-// One CTA = 64 batch rows = two sub-tiles of 32 that ping-pong: while the epilogue warps work on one
-// sub-tile the tensor core runs the other one's 30 MMAs (18 cycles each at N = 32, A in TMEM).
-//   warp 0      : MMA issuer (one elected lane), TMEM allocation
-//   warps 1..3  : x path: TMA (cp.async.bulk.tensor, 3-D map over [B,T,I] by strides) -> raw ring ->
-//                 fp16 hi/lo split -> K-major operand tiles
-//   warps 4..11 : epilogue: tcgen05.ld C, M1, M2 -> gate update in registers (state h lives in registers,
-//                 thread = hidden unit, 16 rows per sub-tile) -> STG h_t (128 B per warp per row) ->
-//                 fp16 split -> 16-byte st.shared into the MN-major operand tile -> fence.proxy.async ->
-//                 mbarrier
+// One CTA = 64 batch rows = two 32-row sub-tiles, each an independent step pipeline (MMA burst -> epilogue -> MMA
+// burst ...) running half a period apart, so the tensor core works on one while the epilogue warps work on the other.
+//   warps 0..15  : epilogue, 8 per sub-tile (4 TMEM lane quadrants x 2 row halves); thread = hidden unit, 16 rows:
+//                  tcgen05.ld CA, CB, M1, M2 -> sum -> gate update on the packed fp32x2 pipe, one MUFU.EX2 and one
+//                  MUFU.RCP per element, state h in registers for all T steps -> fp16 split -> 16-byte st.shared into
+//                  the MN-major operand tile -> fence.proxy.async -> mbarrier -> (then) STG h_t, 128 B per warp per row
+//   warps 16..19 : x path: TMA (cp.async.bulk.tensor, 3-D map over [B,T,I] by the caller's strides), 16 rows and a
+//                  private 4-stage raw ring per warp -> fp16 hi/lo split -> K-major operand tiles (4 buffers)
+//   warps 20..22 : MMA issuers: the 30 MMAs of a sub-tile step, 10 per warp, on one elected lane in a straight-line
+//                  block; TMEM allocation (all 512 columns, so every tcgen05 address is a warp-uniform constant)
+// Measured (tools/tc_trace.cu, profiles/r01_tc_fwd_ncu_summary.txt): the kernel is bound by the serial per-step chain
+// of a sub-tile, not by HBM (34 %) or the tensor pipe (35 %).
 #include "fgrnn_kernels.cuh"
 #include "fgrnn_tc_common.cuh"
 
@@ -127,30 +130,38 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
 //   tot = 2^S * pre.   e_g = exp(-(pre + b_g)),  e_u = exp(-2 (pre + b_u));   one MUFU.RCP serves both gates:
 //   r = 1/((1+e_g)(1+e_u));  z = r (1+e_u) = sigmoid(pre + b_g);  c = 2 r (1+e_g) - 1 = tanh(pre + b_u);
 //   h' = z (h - sz c) + (sz + sn) c   ( = z h + (sz (1 - z) + sn) c ).
-// tot is clamped from below (per-unit constant tmin) so that both exponents stay <= 60 and the product stays
-// finite; at the clamp z < 1e-18 and c = -1 to fp32 precision.
-struct EpiConst { float2 kS, k2S, cg, cu, msz, szn, tmin_; float tmin; };
+// ONE_EX2: e_u = e_g^2 * exp(2 (b_g - b_u)) (one MUFU.EX2 per element; chosen per CTA when no unit's biases are more
+// than 8 apart); tot is clamped from below (per-unit constant) so that e_g <= 2^30: z < 1e-9 and c = -1 there.
+struct EpiConst { float2 kS, k2S, cg, cu, cu2, msz, szn; float tmin; };
 #ifndef FGRNN_TC_C_FORM
 #define FGRNN_TC_C_FORM 0       // 1: c = (1 - e_u) * (r a) instead of 2 r a - 1
 #endif
 #ifndef FGRNN_TC_ONE_EX2
 #define FGRNN_TC_ONE_EX2 1      // 1: e_u = e_g^2 * exp(2 (b_g - b_u)) saves one MUFU.EX2 per element
 #endif
+template <bool ONE_EX2>
 __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiConst& k, float2& z, float2& c) {
-  tot.x = fmaxf(tot.x, k.tmin); tot.y = fmaxf(tot.y, k.tmin);
-  const float2 ag = __ffma2_rn(tot, k.kS, k.cg);               // -(pre + b_g) * log2(e)
-  float2 eg, eu;
+  float2 ag, eg, eu;
+  if (ONE_EX2) {
+    // one clamp on tot keeps e_g <= 2^30; e_u = e_g^2 * ratio follows the clamped value consistently (tanh is -1 there)
+    tot.x = fmaxf(tot.x, k.tmin); tot.y = fmaxf(tot.y, k.tmin);
+    ag = __ffma2_rn(tot, k.kS, k.cg);                          // -(pre + b_g) * log2(e)
+  } else {
+    ag = __ffma2_rn(tot, k.kS, k.cg);
+    ag.x = fminf(ag.x, 60.0f); ag.y = fminf(ag.y, 60.0f);      // the two exponents are clamped separately
+  }
 #ifdef TC_EXP_NO_MUFU
   eg = __fmul2_rn(ag, ag);
 #else
   eg.x = ex2_approx(ag.x); eg.y = ex2_approx(ag.y);
 #endif
-#if FGRNN_TC_ONE_EX2
-  eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                   // cu = exp(2 (b_g - b_u))
-#else
-  const float2 au = __ffma2_rn(tot, k.k2S, k.cu);              // -2 (pre + b_u) * log2(e)
-  eu.x = ex2_approx(au.x); eu.y = ex2_approx(au.y);
-#endif
+  if (ONE_EX2) {
+    eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                 // cu = exp(2 (b_g - b_u))
+  } else {
+    float2 au = __ffma2_rn(tot, k.k2S, k.cu2);                 // -2 (pre + b_u) * log2(e)
+    au.x = fminf(au.x, 60.0f); au.y = fminf(au.y, 60.0f);
+    eu.x = ex2_approx(au.x); eu.y = ex2_approx(au.y);
+  }
   const float2 one = make_float2(1.0f, 1.0f);
   const float2 a = __fadd2_rn(eg, one), b = __fadd2_rn(eu, one);
   const float2 ab = __fmul2_rn(a, b);
@@ -195,7 +206,7 @@ struct EpiCtx {
   bool trace;
 };
 
-template <bool HAS_OUT, bool SAVE, bool MASKED>
+template <bool HAS_OUT, bool SAVE, bool MASKED, bool ONE_EX2>
 __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[8]) {
   char* outp = reinterpret_cast<char*>(cx.out);
   float* zp = cx.zs; float* cp = cx.cs;
@@ -225,7 +236,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
 #ifdef TC_EXP_NO_MATH
         hst[g * 4 + q] = tot; z = tot; c = tot;
 #else
-        hst[g * 4 + q] = gate_update2(tot, hst[g * 4 + q], kc, z, c);
+        hst[g * 4 + q] = gate_update2<ONE_EX2>(tot, hst[g * 4 + q], kc, z, c);
 #endif
         split_pair(hst[g * 4 + q], hi[g * 4 + q], lo[g * 4 + q]);
         if (SAVE) {                                      // training forward: z_s, c_s (cu:340-341)
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
   const TcSmemLayout L = tc_smem_layout(I, KI, esz);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
-  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [2][16] max|U|, max|W| per epilogue warp
+  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16] max|U|, max|W|, max|b_g - b_u| per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TC_ROWS;
@@ -482,6 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     // The four warps of a quadrant take 32 k each of U and 16 k each of W; everything is loaded in one batch,
     // the power-of-two scale comes from max|U|, max|W| over the CTA's copy (identical in every CTA).
     float scale_w, unscale;
+    bool wide_bias;
     {
       const int part = ew >> 2;                        // 0..3
       float uv[32], wv[16];
@@ -505,10 +517,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
         mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
         mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
       }
-      if (lane == 0) { red_s[ew] = mu; red_s[16 + ew] = mw; }
+      // a third reduced quantity: the largest gate/update bias distance of any unit (selects the activation form)
+      float bd = part == 0 ? fabsf(__ldg(a.bias_gate + n) - __ldg(a.bias_update + n)) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bd = fmaxf(bd, __shfl_xor_sync(0xffffffffu, bd, o));
+      if (lane == 0) { red_s[ew] = mu; red_s[16 + ew] = mw; red_s[32 + ew] = bd; }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // epilogue warps only
 #pragma unroll
-      for (int w = 0; w < TC_EPI_WARPS; ++w) { mu = fmaxf(mu, red_s[w]); mw = fmaxf(mw, red_s[16 + w]); }
+      for (int w = 0; w < TC_EPI_WARPS; ++w) { mu = fmaxf(mu, red_s[w]); mw = fmaxf(mw, red_s[16 + w]); bd = fmaxf(bd, red_s[32 + w]); }
+      wide_bias = !(bd <= 8.0f);                        // NaN biases also take the plain form
       // accumulators hold 2^S * pre:  h.(U*2^S) and x.(W*2^S); h and x themselves are split unscaled (an fp16
       // subnormal lo part still resolves 2^-24 absolute, i.e. fp32-level for |h| <= 1)
       int S = 40;
@@ -536,6 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     }
 
     EpiConst kc;
+    bool one_ex2;
     {
       const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
       constexpr float LOG2E = 1.4426950408889634f;
@@ -543,16 +561,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
       const float kS = -LOG2E * unscale, cg = -LOG2E * bgv;
       kc.kS = make_float2(kS, kS); kc.cg = make_float2(cg, cg);
       kc.msz = make_float2(-sz, -sz); kc.szn = make_float2(sz + sn, sz + sn);
-#if FGRNN_TC_ONE_EX2
-      const float ratio = fminf(fmaxf(expf(2.0f * (bgv - buv)), 1e-9f), 1e9f);
-      kc.cu = make_float2(ratio, ratio); kc.k2S = kc.kS;
-      // e_g <= 2^30 keeps (1+e_g)(1+e_g^2 ratio) finite
+      const float k2S = -2.0f * LOG2E * unscale, cu2 = -2.0f * LOG2E * buv;
+      kc.k2S = make_float2(k2S, k2S); kc.cu2 = make_float2(cu2, cu2);
+      // e_u = e_g^2 * exp(2 (b_g - b_u)) saves one MUFU.EX2 per element; if any unit's two biases are more than 8
+      // apart (exp(16) ~ 9e6 still leaves head-room) the whole CTA takes the two-EX2 form instead
+      one_ex2 = FGRNN_TC_ONE_EX2 && !wide_bias;
+      const float ratio = one_ex2 ? expf(2.0f * (bgv - buv)) : 1.0f;
+      kc.cu = make_float2(ratio, ratio);
+      // one-EX2 form: tot >= tmin  <=>  e_g <= 2^30, so (1+e_g)(1+e_g^2 ratio) stays finite (ratio <= e^16);
+      // the two-EX2 form clamps each exponent at 60 instead
       kc.tmin = (30.0f - cg) / kS;
-#else
-      const float k2S = -2.0f * LOG2E * unscale, cu = -2.0f * LOG2E * buv;
-      kc.k2S = make_float2(k2S, k2S); kc.cu = make_float2(cu, cu);
-      kc.tmin = fmaxf((60.0f - cg) / kS, (60.0f - cu) / k2S);       // tot >= tmin  <=>  both exponents <= 60
-#endif
     }
 
     // state: this thread owns h[row][n] for 16 rows of its sub-tile, kept as row pairs for the fp32x2 pipe
@@ -591,16 +609,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
     cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = (ew & 11) == 0; cx.s = es;
     const bool masked = row0 + TC_ROWS > d.B;
-    const int variant = (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
+    const int variant = (one_ex2 ? 8 : 0) | (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
-      case 0: epilogue_loop<false, false, false>(cx, kc, hst); break;
-      case 1: epilogue_loop<false, false, true>(cx, kc, hst); break;
-      case 2: epilogue_loop<false, true, false>(cx, kc, hst); break;
-      case 3: epilogue_loop<false, true, true>(cx, kc, hst); break;
-      case 4: epilogue_loop<true, false, false>(cx, kc, hst); break;
-      case 5: epilogue_loop<true, false, true>(cx, kc, hst); break;
-      case 6: epilogue_loop<true, true, false>(cx, kc, hst); break;
-      default: epilogue_loop<true, true, true>(cx, kc, hst); break;
+      case 0: epilogue_loop<false, false, false, false>(cx, kc, hst); break;
+      case 1: epilogue_loop<false, false, true, false>(cx, kc, hst); break;
+      case 2: epilogue_loop<false, true, false, false>(cx, kc, hst); break;
+      case 3: epilogue_loop<false, true, true, false>(cx, kc, hst); break;
+      case 4: epilogue_loop<true, false, false, false>(cx, kc, hst); break;
+      case 5: epilogue_loop<true, false, true, false>(cx, kc, hst); break;
+      case 6: epilogue_loop<true, true, false, false>(cx, kc, hst); break;
+      case 7: epilogue_loop<true, true, true, false>(cx, kc, hst); break;
+      case 8: epilogue_loop<false, false, false, true>(cx, kc, hst); break;
+      case 9: epilogue_loop<false, false, true, true>(cx, kc, hst); break;
+      case 10: epilogue_loop<false, true, false, true>(cx, kc, hst); break;
+      case 11: epilogue_loop<false, true, true, true>(cx, kc, hst); break;
+      case 12: epilogue_loop<true, false, false, true>(cx, kc, hst); break;
+      case 13: epilogue_loop<true, false, true, true>(cx, kc, hst); break;
+      case 14: epilogue_loop<true, true, false, true>(cx, kc, hst); break;
+      default: epilogue_loop<true, true, true, true>(cx, kc, hst); break;
     }
     TC_CTA_TIME(2);
     if (a.h_last) {

@@ -182,3 +182,19 @@ def test_tcgen05_last_state_only_and_chunked_carry():
     # a strided (non-contiguous) time slice goes through the TMA map without a copy
     c, _, _, _ = engine.forward(x[:, 11:], params, ha, **kw)
     assert torch.equal(c, b)
+
+
+def test_tcgen05_extreme_biases_and_saturated_gates():
+    """Units whose gate and update biases are far apart leave the shared-exponential form (e_u = e_g^2 * ratio)
+    for the two-exponential form; saturated gates (|pre| ~ 40) must stay finite."""
+    from kws_b200 import _lib, engine
+    torch.manual_seed(8)
+    p = O.init_params(32, 128)
+    p.bias_gate[0, :8] += 12.0; p.bias_update[0, 8:16] -= 11.0; p.bias_gate[0, 16:24] -= 30.0; p.bias_update[0, 24:32] += 25.0
+    x = torch.randn(50, 7, 32)
+    x[:5] *= 8.0                                            # |pre| up to ~20 on top of the bias offsets
+    ref = O.unroll(x, p, None, True)
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    out = engine.forward(x.to(dev()), params, None, layout="IH", batch_first=True, force_path=_lib.PATH_TCGEN05)[0]
+    assert torch.isfinite(out).all()
+    assert state_ratio(out, ref) <= 1.0
