@@ -198,3 +198,25 @@ def test_tcgen05_extreme_biases_and_saturated_gates():
     out = engine.forward(x.to(dev()), params, None, layout="IH", batch_first=True, force_path=_lib.PATH_TCGEN05)[0]
     assert torch.isfinite(out).all()
     assert state_ratio(out, ref) <= 1.0
+
+
+def test_tcgen05_backward_with_bf16_inputs():
+    """bf16 x (config 5 style): the dW contraction reads the bf16 tile directly (no lo part); parity against
+    autograd of the oracle fed the same bf16-rounded inputs."""
+    from kws_b200 import engine
+    from gpu_helpers import grad_ratio
+    torch.manual_seed(31)
+    B, T, I = 90, 6, 32
+    p = O.init_params(I, 128)
+    x = torch.randn(B, T, I).bfloat16()
+    go = torch.randn(B, T, 128) / B
+    gref = O.autograd_grads(x.float(), p, torch.zeros(B, 128), go, True)
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    xg, gog = x.to(dev()), go.to(dev())
+    out, z_s, c_s, _ = engine.forward(xg, params, None, layout="IH", batch_first=True, save_for_backward=True)
+    ref = O.unroll(x.float(), p, None, True)
+    assert state_ratio(out, ref) <= 1.0
+    g = engine.backward(gog, xg, out, z_s, c_s, params, None, layout="IH", batch_first=True)
+    torch.cuda.synchronize()
+    for k in p.tensors():
+        assert grad_ratio(g[k], gref[k]) <= 1.0, (k, grad_ratio(g[k], gref[k]))
