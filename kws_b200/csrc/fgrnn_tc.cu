@@ -30,6 +30,8 @@
 //                  block; TMEM allocation (all 512 columns, so every tcgen05 address is a warp-uniform constant)
 // Measured (tools/tc_trace.cu, profiles/r01_tc_fwd_ncu_summary.txt): the kernel is bound by the serial per-step chain
 // of a sub-tile, not by HBM (34 %) or the tensor pipe (35 %).
+#include <cstdlib>
+
 #include "fgrnn_kernels.cuh"
 #include "fgrnn_tc_common.cuh"
 
@@ -45,11 +47,8 @@ __device__ __forceinline__ float2 s_fmul2(float2 a, float2 b) { return make_floa
 #endif
 
 constexpr int TC_H = 128;                      // hidden size = UMMA M
-constexpr int TC_NS = 32;                      // batch rows per sub-tile = UMMA N
 constexpr int TC_NT = 2;                       // sub-tiles per CTA
-constexpr int TC_ROWS = TC_NS * TC_NT;         // 64 batch rows per CTA
-constexpr int TC_CONV_WARPS = 4;                // each owns 16 rows of the x tile: own TMA box, own raw ring
-constexpr int TC_CONV_ROWS = 16;
+constexpr int TC_CONV_WARPS = 4;                // each owns a quarter of the CTA's rows: own TMA box, own raw ring
 constexpr int TC_XBUF = 4;                      // x operand tile buffers (the converters run up to 3 steps ahead)
 constexpr int TC_EPI_WARPS = 16;                // 8 per sub-tile: 4 TMEM lane quadrants x 2 row halves
 constexpr int TC_MMA_WARPS = 3;                 // the 30 MMAs of a sub-tile step are issued by three warps, 10 each
@@ -58,7 +57,6 @@ constexpr int TC_RAW_STAGES = 4;
 constexpr int TC_MAX_KI = 64;                  // input features padded to a multiple of 16, <= 64
 // tensor-memory column map
 constexpr int TM_U_HI = 0, TM_U_LO = 64, TM_W_HI = 128, TM_W_LO = 160, TM_ACC = 192;
-constexpr int TM_ACC_PER_TILE = 4 * TC_NS;     // CA | CB | M1 | M2
 constexpr int TC_TMEM_COLS = 512;
 #ifndef TC_CRIT_WAIT
 #define TC_CRIT_WAIT mbar_wait      // waits on the step-critical path (mbar_wait_poll = spin without suspend hint)
@@ -83,24 +81,6 @@ __device__ __forceinline__ unsigned long long tc_globaltimer() { unsigned long l
 #define TC_CTA_TIME(slot) do { } while (0)
 #endif
 
-// ---- operand layouts (SWIZZLE_NONE canonical layouts, 128-byte core matrices) -------------------
-// x tile, K-major [rows][KI]: core matrix = 8 rows x 16 B (8 k);  next 8 k: +128 B (LBO);  next 8 rows: +(KI/8)*128 B (SBO)
-__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr, int KI) {
-  const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((KI >> 3) * 128) >> 4;
-  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
-}
-// h tile, MN-major [k][rows]: core matrix = 8 k x 16 B (8 rows);  next 8 rows: +128 B (SBO);  next 8 k: +(NS/8)*128 B (LBO)
-__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t smem_addr) {
-  const uint64_t sbo = 128 >> 4, lbo = (uint64_t)((TC_NS >> 3) * 128) >> 4;
-  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
-}
-constexpr uint32_t TC_H_KSTEP = (2 * (TC_NS >> 3) * 128) >> 4;     // descriptor advance per 16 k of the h tile
-constexpr uint32_t TC_X_KSTEP = 256 >> 4;                          // ... of the x tile
-// kind::f16: D fp32, A/B fp16, A K-major (TMEM), N = 32, M = 128; bit 16 = B is MN-major
-constexpr uint32_t TC_IDESC_X = (1u << 4) | ((uint32_t)(TC_NS >> 3) << 17) | ((uint32_t)(TC_H >> 4) << 24);
-constexpr uint32_t TC_IDESC_H = TC_IDESC_X | (1u << 16);
-
-
 struct TcArgs {
   SmemFwdArgs f;
   int KI;               // I rounded up to a multiple of 16
@@ -111,7 +91,36 @@ struct TcSmemLayout {
   int h_op, x_op, raw, bars, misc, total;
   int x_tile_bytes, raw_stage_bytes;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
+// Everything below depends on the sub-tile width NS = UMMA N (32 rows for large batches; 16 rows when the batch
+// would not fill the SMs otherwise: the per-step chain of a 16-row sub-tile is ~30 % shorter).
+template <int TC_NS>
+struct TcFwd {
+static constexpr int TC_ROWS = TC_NS * TC_NT;          // batch rows per CTA (64 or 32)
+static constexpr int TC_CONV_ROWS = TC_ROWS / TC_CONV_WARPS;   // rows per converter warp / TMA box
+static constexpr int TM_ACC_PER_TILE = 4 * TC_NS;      // CA | CB | M1 | M2
+static constexpr int RPT = TC_NS / 2;                  // rows per epilogue thread (two row halves per sub-tile)
+static constexpr int PAIRS = RPT / 2;                  // row pairs on the packed fp32x2 pipe
+static constexpr int NG = RPT / 8;                     // 8-row groups = 16-byte operand chunks per thread
+
+// ---- operand layouts (SWIZZLE_NONE canonical layouts, 128-byte core matrices) -------------------
+// x tile, K-major [rows][KI]: core matrix = 8 rows x 16 B (8 k);  next 8 k: +128 B (LBO);  next 8 rows: +(KI/8)*128 B (SBO)
+static __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr, int KI) {
+  const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((KI >> 3) * 128) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// h tile, MN-major [k][rows]: core matrix = 8 k x 16 B (8 rows);  next 8 rows: +128 B (SBO);  next 8 k: +(NS/8)*128 B (LBO)
+static __device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t smem_addr) {
+  const uint64_t sbo = 128 >> 4, lbo = (uint64_t)((TC_NS >> 3) * 128) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+static constexpr uint32_t TC_H_KSTEP = (2 * (TC_NS >> 3) * 128) >> 4;     // descriptor advance per 16 k of the h tile
+static constexpr uint32_t TC_X_KSTEP = 256 >> 4;                          // ... of the x tile
+// kind::f16: D fp32, A/B fp16, A K-major (TMEM), N = 32, M = 128; bit 16 = B is MN-major
+static constexpr uint32_t TC_IDESC_X = (1u << 4) | ((uint32_t)(TC_NS >> 3) << 17) | ((uint32_t)(TC_H >> 4) << 24);
+static constexpr uint32_t TC_IDESC_H = TC_IDESC_X | (1u << 16);
+
+
+static __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
   TcSmemLayout L;
   L.x_tile_bytes = TC_NS * KI * 2;
   L.raw_stage_bytes = TC_CONV_ROWS * I * esz;                   // per converter warp
@@ -140,7 +149,7 @@ struct EpiConst { float2 kS, k2S, cg, cu, cu2, msz, szn; float tmin; };
 #define FGRNN_TC_ONE_EX2 1      // 1: e_u = e_g^2 * exp(2 (b_g - b_u)) saves one MUFU.EX2 per element
 #endif
 template <bool ONE_EX2>
-__device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiConst& k, float2& z, float2& c) {
+static __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiConst& k, float2& z, float2& c) {
   float2 ag, eg, eu;
   if (ONE_EX2) {
     // one clamp on tot keeps e_g <= 2^30; e_u = e_g^2 * ratio follows the clamped value consistently (tanh is -1 there)
@@ -181,7 +190,7 @@ __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, const EpiCo
 }
 
 // h (two rows) -> fp16 hi pair and fp16 lo pair (residual, exact subtraction); |h| < 65504
-__device__ __forceinline__ void split_pair(float2 h, uint32_t& hi, uint32_t& lo) {
+static __device__ __forceinline__ void split_pair(float2 h, uint32_t& hi, uint32_t& lo) {
 #ifdef TC_EXP_NO_SPLIT
   hi = __float_as_uint(h.x); lo = __float_as_uint(h.y); return;
 #endif
@@ -207,7 +216,7 @@ struct EpiCtx {
 };
 
 template <bool HAS_OUT, bool SAVE, bool MASKED, bool ONE_EX2>
-__device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[8]) {
+static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[PAIRS]) {
   char* outp = reinterpret_cast<char*>(cx.out);
   float* zp = cx.zs; float* cp = cx.cs;
   const uint32_t row_bytes = cx.out_row * 4u;
@@ -218,9 +227,9 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
 #endif
     tc_fence_after();
     if (cx.trace) TC_TRACE(t, cx.s, 1);
-    uint32_t hi[8], lo[8];
+    uint32_t hi[PAIRS], lo[PAIRS];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < NG; ++g) {
       float va[8], vb[8], v1[8], v2[8];
       tmem_ld8(cx.acc + g * 8, va);
       tmem_ld8(cx.acc + TC_NS + g * 8, vb);
@@ -246,10 +255,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
         }
       }
     }
-    *reinterpret_cast<uint4*>(cx.hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(cx.hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {                     // one 16-byte chunk (8 rows of this unit) per group, hi and lo tile
+      *reinterpret_cast<uint4*>(cx.hop + g * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2 + g * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+    }
     if (cx.trace) TC_TRACE(t, cx.s, 3);
     // hand h_t to the tensor core first: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would
     // wait for the global stores too, so those are issued after the arrive and drain behind the next wait
@@ -260,7 +270,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
     if (cx.trace) TC_TRACE(t, cx.s, 4);
     if (HAS_OUT) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < PAIRS; ++q) {
         if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
         if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
       }
@@ -278,7 +288,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const EpiConst& 
 //   role 2 -> M1 : hi.hi of x.W and of h.U k-steps 0..2;   M2 : hi.hi of h.U k-steps 3..7
 // Every TMEM column and descriptor offset is a compile-time constant on top of uniform bases.
 template <int ROLE, int NKX, bool X_HAS_LO>
-__device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
+static __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
   if (ROLE == 0) {
 #pragma unroll
     for (int ks = 0; ks < NKX; ++ks) {
@@ -307,7 +317,7 @@ __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, 
 }
 
 template <int ROLE>
-__device__ __forceinline__ void issue_subtile_dispatch(int variant, uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
+static __device__ __forceinline__ void issue_subtile_dispatch(int variant, uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
   switch (variant) {
     case 0: issue_subtile_mmas<ROLE, 1, false>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
     case 1: issue_subtile_mmas<ROLE, 1, true>(tmem, acc, dXhi, dXlo, dHhi, dHlo); break;
@@ -320,7 +330,7 @@ __device__ __forceinline__ void issue_subtile_dispatch(int variant, uint32_t tme
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
+static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& xmap) {
   extern __shared__ __align__(128) unsigned char sm[];
   const SmemFwdArgs& a = ta.f;
   const Dims d = a.d;
@@ -485,7 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     const int ew = warp;                               // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access (= ew & 3)
     const int es = (ew >> 2) & 1;                      // the sub-tile this warp serves
-    const int rh = ew >> 3;                            // which 16 of the sub-tile's 32 rows
+    const int rh = ew >> 3;                            // which half of the sub-tile's rows
     const int n = quad * 32 + lane;                    // hidden unit = TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
@@ -574,23 +584,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     }
 
     // state: this thread owns h[row][n] for 16 rows of its sub-tile, kept as row pairs for the fp32x2 pipe
-    float2 hst[8];
-    unsigned char* hop = sm + L.h_op + es * (2 * TC_NS * TC_H * 2) + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
-    const int first_row = row0 + es * TC_NS + rh * 16;
+    float2 hst[PAIRS];
+    unsigned char* hop = sm + L.h_op + es * (2 * TC_NS * TC_H * 2) + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * NG) * 128 + (n & 7) * 16;
+    const int first_row = row0 + es * TC_NS + rh * RPT;
     {
-      uint32_t hi[8], lo[8];
+      uint32_t hi[PAIRS], lo[PAIRS];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < PAIRS; ++q) {
         const int row = first_row + 2 * q;
         const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
         const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
         hst[q] = make_float2(v0, v1);
         split2(v0, v1, 1.0f, hi[q], lo[q]);
       }
-      *reinterpret_cast<uint4*>(hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        *reinterpret_cast<uint4*>(hop + g * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+        *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2 + g * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -601,7 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     TC_CTA_TIME(1);
     EpiCtx cx;
     cx.bar_dfull = bar(B_DFULL + es); cx.bar_hready = bar(B_HREADY + es);
-    cx.acc = tmem + lane_base + TM_ACC + es * TM_ACC_PER_TILE + rh * 16;
+    cx.acc = tmem + lane_base + TM_ACC + es * TM_ACC_PER_TILE + rh * RPT;
     cx.hop = hop;
     cx.out = a.out ? a.out + (size_t)first_row * a.osb + n : nullptr;
     cx.zs = a.save_z ? a.save_z + (size_t)first_row * TC_H + n : nullptr;
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
     TC_CTA_TIME(2);
     if (a.h_last) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < RPT; ++j) {
         const int row = first_row + j;
         if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
       }
@@ -640,6 +651,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, 
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, TC_TMEM_COLS);
+}
+
+};   // struct TcFwd
+
+template <int NS>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
+  TcFwd<NS>::run(ta, xmap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,22 +678,33 @@ bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, in
   return xsb > 0 && xst > 0;
 }
 
-int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
+template <int NS>
+static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
+  using K = TcFwd<NS>;
   const Dims& d = a.d;
-  if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
   TcArgs ta{};
   ta.f = a;
   ta.KI = (d.I + 15) & ~15;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
   CUtensorMap map;
-  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, TC_CONV_ROWS, &ta.x_time_outer);
+  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, K::TC_CONV_ROWS, &ta.x_time_outer);
   if (rc) return rc;
-  const TcSmemLayout L = tc_smem_layout(d.I, ta.KI, esz);
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  const unsigned grid = (unsigned)((d.B + TC_ROWS - 1) / TC_ROWS);
-  tc_fwd_kernel<<<grid, TC_THREADS, L.total, stream>>>(ta, map);
+  const TcSmemLayout L = K::tc_smem_layout(d.I, ta.KI, esz);
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const unsigned grid = (unsigned)((d.B + K::TC_ROWS - 1) / K::TC_ROWS);
+  tc_fwd_kernel<NS><<<grid, TC_THREADS, L.total, stream>>>(ta, map);
   FGRNN_LAUNCH_CHECK("tc_fwd_kernel");
   return FGRNN_OK;
+}
+
+// Sub-tile width: the per-step chain of a CTA does not depend on how many SMs are busy, so as long as the batch
+// fits in one wave of 32-row CTAs (two 16-row sub-tiles) those are faster; larger batches take 64-row CTAs.
+// FGRNN_TC_NS=16|32 overrides (tests, benchmarks).
+int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
+  if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
+  int ns = a.d.B <= 148 * 32 ? 16 : 32;
+  if (const char* e = getenv("FGRNN_TC_NS")) { if (atoi(e) == 16) ns = 16; else if (atoi(e) == 32) ns = 32; }
+  return ns == 16 ? launch_tc_fwd_ns<16>(a, stream) : launch_tc_fwd_ns<32>(a, stream);
 }
 
 }  // namespace fgrnn
