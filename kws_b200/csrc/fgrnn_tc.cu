@@ -47,12 +47,9 @@ __device__ __forceinline__ float2 s_fmul2(float2 a, float2 b) { return make_floa
 #endif
 
 constexpr int TC_H = 128;                      // hidden size = UMMA M
-constexpr int TC_NT = 2;                       // sub-tiles per CTA
 constexpr int TC_CONV_WARPS = 4;                // each owns a quarter of the CTA's rows: own TMA box, own raw ring
 constexpr int TC_XBUF = 4;                      // x operand tile buffers (the converters run up to 3 steps ahead)
-constexpr int TC_EPI_WARPS = 16;                // 8 per sub-tile: 4 TMEM lane quadrants x 2 row halves
-constexpr int TC_MMA_WARPS = 3;                 // the 30 MMAs of a sub-tile step are issued by three warps, 10 each
-constexpr int TC_THREADS = 32 * (TC_MMA_WARPS + TC_CONV_WARPS + TC_EPI_WARPS);   // 736
+constexpr int TC_EPI_WARPS = 16;                // 4 TMEM lane quadrants x (sub-tiles x row halves)
 constexpr int TC_RAW_STAGES = 4;
 constexpr int TC_MAX_KI = 64;                  // input features padded to a multiple of 16, <= 64
 // tensor-memory column map
@@ -60,6 +57,15 @@ constexpr int TM_U_HI = 0, TM_U_LO = 64, TM_W_HI = 128, TM_W_LO = 160, TM_ACC = 
 constexpr int TC_TMEM_COLS = 512;
 #ifndef TC_CRIT_WAIT
 #define TC_CRIT_WAIT mbar_wait      // waits on the step-critical path (mbar_wait_poll = spin without suspend hint)
+#endif
+#ifndef TC_NT4_ROLES
+#define TC_NT4_ROLES 2
+#endif
+#ifndef TC_NT4_SPS
+#define TC_NT4_SPS 2
+#endif
+#ifndef TC_STAGGER2_NS
+#define TC_STAGGER2_NS (TC_STAGGER_NS / 2)
 #endif
 #ifndef TC_STAGGER_NS
 #define TC_STAGGER_NS 500
@@ -93,12 +99,21 @@ struct TcSmemLayout {
 };
 // Everything below depends on the sub-tile width NS = UMMA N (32 rows for large batches; 16 rows when the batch
 // would not fill the SMs otherwise: the per-step chain of a 16-row sub-tile is ~30 % shorter).
-template <int TC_NS>
+// TC_NT = sub-tiles per CTA: 2 (one set of three MMA warps alternating between them) or 4 (two sets of two MMA
+// warps, each set alternating between its own pair of sub-tiles; 16-row sub-tiles only: 4 x 4 x 16 accumulator columns).
+template <int TC_NS, int TC_NT>
 struct TcFwd {
+static_assert(TC_NT == 2 || (TC_NT == 4 && TC_NS == 16), "sub-tile configuration");
+static constexpr int TC_MMA_ROLES = TC_NT == 2 ? 3 : TC_NT4_ROLES;       // warps sharing the 30 MMAs of a sub-tile step
+static constexpr int TC_SPS = TC_NT == 2 ? 2 : TC_NT4_SPS;     // sub-tiles served by one set of MMA warps
+static constexpr int TC_MMA_SETS = TC_NT / TC_SPS;
+static constexpr int TC_MMA_WARPS = TC_MMA_ROLES * TC_MMA_SETS;
+static constexpr int TC_THREADS = 32 * (TC_MMA_WARPS + TC_CONV_WARPS + TC_EPI_WARPS);   // 736 or 768
 static constexpr int TC_ROWS = TC_NS * TC_NT;          // batch rows per CTA (64 or 32)
+static constexpr int TC_RH = TC_EPI_WARPS / TC_NT / 4; // row halves per sub-tile (epilogue warps per lane quadrant)
 static constexpr int TC_CONV_ROWS = TC_ROWS / TC_CONV_WARPS;   // rows per converter warp / TMA box
 static constexpr int TM_ACC_PER_TILE = 4 * TC_NS;      // CA | CB | M1 | M2
-static constexpr int RPT = TC_NS / 2;                  // rows per epilogue thread (two row halves per sub-tile)
+static constexpr int RPT = TC_NS / TC_RH;              // rows per epilogue thread
 static constexpr int PAIRS = RPT / 2;                  // row pairs on the packed fp32x2 pipe
 static constexpr int NG = RPT / 8;                     // 8-row groups = 16-byte operand chunks per thread
 
@@ -286,10 +301,11 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
 //   role 0 -> CA : lo terms of x.W (W_lo.x_hi, W_hi.x_lo) and of h.U k-steps 0..2 (U_lo.h_hi, U_hi.h_lo)
 //   role 1 -> CB : lo terms of h.U k-steps 3..7
 //   role 2 -> M1 : hi.hi of x.W and of h.U k-steps 0..2;   M2 : hi.hi of h.U k-steps 3..7
+// With two issuing warps per sub-tile (four sub-tiles per CTA): role 3 = CA + M1, role 4 = CB + M2, 15 MMAs each.
 // Every TMEM column and descriptor offset is a compile-time constant on top of uniform bases.
 template <int ROLE, int NKX, bool X_HAS_LO>
 static __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
-  if (ROLE == 0) {
+  if (ROLE == 0 || ROLE == 3 || ROLE == 5) {
 #pragma unroll
     for (int ks = 0; ks < NKX; ++ks) {
       umma_ts1(acc, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
@@ -300,17 +316,21 @@ static __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_
       umma_ts1(acc, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
       umma_ts1(acc, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
     }
-  } else if (ROLE == 1) {
+  }
+  if (ROLE == 1 || ROLE == 4 || ROLE == 5) {
 #pragma unroll
     for (int ks = 3; ks < TC_H / 16; ++ks) {
       umma_ts1(acc + TC_NS, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
       umma_ts1(acc + TC_NS, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
     }
-  } else {
+  }
+  if (ROLE == 2 || ROLE == 3 || ROLE == 5) {
 #pragma unroll
     for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc + 2 * TC_NS, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) umma_ts1(acc + 2 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+  }
+  if (ROLE == 2 || ROLE == 4 || ROLE == 5) {
 #pragma unroll
     for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts1(acc + 3 * TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
   }
@@ -346,7 +366,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   const bool hi_layout = a.layout == FGRNN_LAYOUT_HI;
   // barrier map
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  const int B_HREADY = 0, B_DFULL = 2, B_XFULL = 4, B_XEMPTY = 8, B_RAWFULL = 12;   // RAWFULL: [conv warp][stage]
+  const int B_HREADY = 0, B_DFULL = 4, B_XFULL = 8, B_XEMPTY = 12, B_RAWFULL = 16;   // RAWFULL: [conv warp][stage]
 
   // ---- prologue ---------------------------------------------------------------------------------
   TC_CTA_TIME(0);
@@ -354,7 +374,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   constexpr int W_CONV0 = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + TC_CONV_WARPS;
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), TC_TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS / TC_NT); mbar_init(bar(B_DFULL + s), TC_MMA_WARPS); }
+    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS / TC_NT); mbar_init(bar(B_DFULL + s), TC_MMA_ROLES); }
     for (int b = 0; b < TC_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TC_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TC_MMA_WARPS); }
     for (int st = 0; st < TC_CONV_WARPS * TC_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
     fence_mbar_init();
@@ -368,8 +388,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   constexpr uint32_t tmem = 0u;
 
   if (warp >= W_MMA) {
-    // =========================== MMA issuers (three warps, 10 MMAs each per sub-tile step) ========
-    const int role = warp - W_MMA;
+    // =========================== MMA issuers ======================================================
+    // a set of TC_MMA_ROLES warps shares the 30 MMAs of a sub-tile step and alternates between two sub-tiles
+    const int set = (warp - W_MMA) / TC_MMA_ROLES, role = (warp - W_MMA) % TC_MMA_ROLES;
     const bool leader = elect_one();                   // the same lane issues every MMA and commit of this warp
     tc_fence_before();
     __syncthreads();                                   // weights in TMEM, h_{-1} / x_0 tiles under way
@@ -381,29 +402,38 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     const uint64_t dX0 = make_desc_kmajor(smem_u32(sm + L.x_op), KI);
     const uint32_t xlo_step = (uint32_t)L.x_tile_bytes >> 4, xtile_step = 2 * xlo_step, xbuf_step = TC_NT * xtile_step;
     const int variant = (nkx - 1) * 2 + (x_has_lo ? 1 : 0);
+    if (set) __nanosleep(set * TC_STAGGER2_NS);           // second set: a quarter period behind the first
     for (int t = 0; t < d.T; ++t) {
       const int xb = t % TC_XBUF;
       mbar_wait(bar(B_XFULL + xb), (t / TC_XBUF) & 1); // x_t operand tiles written
 #pragma unroll
-      for (int s = 0; s < TC_NT; ++s) {
+      for (int ss = 0; ss < TC_SPS; ++ss) {
+        const int s = set * TC_SPS + ss;
         const uint64_t dXhi = dX0 + (uint64_t)(xb * xbuf_step + s * xtile_step), dXlo = dXhi + xlo_step;
         const uint64_t dHhi = dH0 + (uint64_t)(s * htile_step), dHlo = dHhi + hlo_step;
         const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
-        if (role == 0) TC_TRACE(t, s, 8);
+        if (role == 0 && set == 0) TC_TRACE(t, s, 8);
         TC_CRIT_WAIT(bar(B_HREADY + s), t & 1);        // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
-        if (role == 0) TC_TRACE(t, s, 9);
+        if (role == 0 && set == 0) TC_TRACE(t, s, 9);
         if (leader) {
-          if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
-          else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
-          else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          if (TC_MMA_ROLES == 3) {
+            if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+            else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+            else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          } else if (TC_MMA_ROLES == 1) {
+            issue_subtile_dispatch<5>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          } else {
+            if (role == 0) issue_subtile_dispatch<3>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+            else issue_subtile_dispatch<4>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          }
           umma_commit1(bar(B_DFULL + s));              // implies tcgen05.fence::before_thread_sync
         }
         __syncwarp();
-        if (role == 0) TC_TRACE(t, s, 10);
+        if (role == 0 && set == 0) TC_TRACE(t, s, 10);
         // start the two sub-tile pipelines half a period apart so that one is in its MMA phase while the
         // other is in its epilogue (they keep the offset: nothing couples them but shared pipes)
-        if (t == 0 && s == 0) __nanosleep(TC_STAGGER_NS);
+        if (t == 0 && ss == 0 && TC_SPS > 1) __nanosleep(TC_STAGGER_NS);
       }
       if (leader) umma_commit1(bar(B_XEMPTY + xb));    // this warp's MMAs have consumed the x_t tiles
       __syncwarp();
@@ -494,8 +524,8 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     // =========================== epilogue warps ===================================================
     const int ew = warp;                               // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access (= ew & 3)
-    const int es = (ew >> 2) & 1;                      // the sub-tile this warp serves
-    const int rh = ew >> 3;                            // which half of the sub-tile's rows
+    const int es = (ew >> 2) % TC_NT;                  // the sub-tile this warp serves
+    const int rh = (ew >> 2) / TC_NT;                  // which part of the sub-tile's rows
     const int n = quad * 32 + lane;                    // hidden unit = TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
@@ -655,9 +685,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
 
 };   // struct TcFwd
 
-template <int NS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
-  TcFwd<NS>::run(ta, xmap);
+template <int NS, int NT>
+__global__ void __launch_bounds__((TcFwd<NS, NT>::TC_THREADS), 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
+  TcFwd<NS, NT>::run(ta, xmap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -678,9 +708,9 @@ bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, in
   return xsb > 0 && xst > 0;
 }
 
-template <int NS>
+template <int NS, int NT>
 static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
-  using K = TcFwd<NS>;
+  using K = TcFwd<NS, NT>;
   const Dims& d = a.d;
   TcArgs ta{};
   ta.f = a;
@@ -690,21 +720,26 @@ static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
   const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, K::TC_CONV_ROWS, &ta.x_time_outer);
   if (rc) return rc;
   const TcSmemLayout L = K::tc_smem_layout(d.I, ta.KI, esz);
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const unsigned grid = (unsigned)((d.B + K::TC_ROWS - 1) / K::TC_ROWS);
-  tc_fwd_kernel<NS><<<grid, TC_THREADS, L.total, stream>>>(ta, map);
+  tc_fwd_kernel<NS, NT><<<grid, K::TC_THREADS, L.total, stream>>>(ta, map);
   FGRNN_LAUNCH_CHECK("tc_fwd_kernel");
   return FGRNN_OK;
 }
 
-// Sub-tile width: the per-step chain of a CTA does not depend on how many SMs are busy, so as long as the batch
-// fits in one wave of 32-row CTAs (two 16-row sub-tiles) those are faster; larger batches take 64-row CTAs.
-// FGRNN_TC_NS=16|32 overrides (tests, benchmarks).
+// Tile configuration.  The per-step chain of a CTA does not depend on how many SMs are busy, and a tcgen05.mma costs
+// the same ~19 cycles for N = 16 and N = 32, so:
+//   batch fits one wave of 32-row CTAs  -> 2 x 16-row sub-tiles (shortest chain: ~2400 cycles per step);
+//   larger batches                      -> 4 x 16-row sub-tiles, two MMA warp sets (~3000 cycles per step for 64 rows,
+//                                          the tensor pipe ~75 % busy), 5-8 % faster than 2 x 32-row sub-tiles.
+// FGRNN_TC_NS=16|32 and FGRNN_TC_NT=2|4 override (tests, benchmarks); NT=4 implies NS=16.
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
-  int ns = a.d.B <= 148 * 32 ? 16 : 32;
-  if (const char* e = getenv("FGRNN_TC_NS")) { if (atoi(e) == 16) ns = 16; else if (atoi(e) == 32) ns = 32; }
-  return ns == 16 ? launch_tc_fwd_ns<16>(a, stream) : launch_tc_fwd_ns<32>(a, stream);
+  int ns = 16, nt = a.d.B <= 148 * 32 ? 2 : 4;
+  if (const char* e = getenv("FGRNN_TC_NT")) { if (atoi(e) == 4) nt = 4; else if (atoi(e) == 2) nt = 2; }
+  if (const char* e = getenv("FGRNN_TC_NS")) { if (atoi(e) == 32) { ns = 32; nt = 2; } }
+  if (nt == 4) return launch_tc_fwd_ns<16, 4>(a, stream);
+  return ns == 16 ? launch_tc_fwd_ns<16, 2>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);
 }
 
 }  // namespace fgrnn

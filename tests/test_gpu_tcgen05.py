@@ -53,6 +53,20 @@ def test_tcgen05_forward_vs_oracle(B, T, I, layout, h0):
     assert torch.equal(last, out[:, -1])
 
 
+@pytest.mark.parametrize("ns,nt", [("16", "2"), ("16", "4"), ("32", "2")])
+def test_tcgen05_forward_every_tile_configuration(monkeypatch, ns, nt):
+    """The launcher picks 2x16-row sub-tiles for one-wave batches and 4x16 beyond; FGRNN_TC_NS / FGRNN_TC_NT pin a
+    configuration.  All three (incl. the 2x32 variant) must meet the tolerance on ragged, multi-CTA, saved-gate runs."""
+    monkeypatch.setenv("FGRNN_TC_NS", ns)
+    monkeypatch.setenv("FGRNN_TC_NT", nt)
+    for (B, T, I, layout, h0, save) in [(77, 9, 32, "HI", True, False), (300, 17, 16, "IH", False, True), (33, 4, 24, "IH", True, False)]:
+        out, last, ref, z_s, c_s = _run(B, T, I, layout, h0, seed=21 + B, save=save)
+        assert state_ratio(out, ref) <= 1.0, (ns, nt, B)
+        assert torch.equal(last, out[:, -1])
+        if save:
+            assert float(z_s.min()) >= 0.0 and float(z_s.max()) <= 1.0 and float(c_s.abs().max()) <= 1.0
+
+
 def test_tcgen05_time_major_and_saved_gates():
     out, last, ref, z_s, c_s = _run(70, 6, 32, "HI", True, seed=3, batch_first=False, save=True)
     assert state_ratio(out, ref) <= 1.0

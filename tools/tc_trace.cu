@@ -1,7 +1,9 @@
 // Developer tool (not part of the product): runs the tcgen05 forward kernel standalone on the C2 shape,
 // times it with CUDA events and prints the in-kernel clock64 trace of CTA 0 (steps 16..19).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I kws_b200/csrc -o tools/tc_trace tools/tc_trace.cu
+#ifndef NO_TRACE
 #define FGRNN_TC_TRACE
+#endif
 #include "../kws_b200/csrc/fgrnn_tc.cu"
 
 #include <cstdarg>
@@ -42,7 +44,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch_tc_fwd(a, 0);
   cudaDeviceSynchronize();
-  const int reps = 10;
+  const int reps = 50;
   cudaEventRecord(e0);
   for (int i = 0; i < reps; ++i) launch_tc_fwd(a, 0);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
@@ -77,6 +79,7 @@ int main(int argc, char** argv) {
       printf("accuracy vs fp64 over %d rows: max |err| / (1e-6 + 1e-5 |h|) = %.3f\n", R, worst);
     }
   }
+#ifdef FGRNN_TC_TRACE
   {
     const int nc = (B + 63) / 64 < 1024 ? (B + 63) / 64 : 1024;
     std::vector<unsigned long long> ct(1024 * 4);
@@ -104,5 +107,6 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 16; ++k) if (names[k][0] && tr[(t * 2 + s) * 16 + k]) printf(" %s %lld", names[k], tr[(t * 2 + s) * 16 + k] - base);
       printf("\n");
     }
+#endif
   return 0;
 }
