@@ -287,32 +287,42 @@ int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream) {
 // (one 16 KB TMA box per array, 3-D maps over the caller's strides).  The bias / zeta / nu sums
 // live in per-thread registers for the whole kernel and leave as one partial row per CTA.
 // =============================================================================================
-constexpr int BR_H = 128, BR_NS = 32, BR_NT = 2, BR_ROWS = BR_NS * BR_NT;
+constexpr int BR_H = 128, BR_NT = 2;
 constexpr int BR_EPI_WARPS = 16, BR_MMA_WARPS = 3;
 constexpr int BR_W_PROD = BR_EPI_WARPS, BR_W_MMA = BR_EPI_WARPS + 1;
 constexpr int BR_THREADS = 32 * (BR_EPI_WARPS + 1 + BR_MMA_WARPS);      // 640
-constexpr int BR_STAGES = 3;
-constexpr int BR_ARR = BR_NS * BR_H * 4;                                // one [32][128] fp32 tile
-constexpr int BR_STAGE = 4 * BR_ARR;                                    // g | z | c | h_{t-1}
-constexpr int BR_OPT = BR_NS * BR_H * 2;                                // one bf16 operand tile
-constexpr int BR_TM_U_HI = 0, BR_TM_U_LO = 64, BR_TM_ACC = 128, BR_TM_ACC_PER_TILE = 4 * BR_NS;
-constexpr uint32_t BR_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BR_NS >> 3) << 17) | ((uint32_t)(BR_H >> 4) << 24);
-constexpr uint32_t BR_KSTEP = (2 * (BR_NS >> 3) * 128) >> 4;
-
+constexpr int BR_TM_U_HI = 0, BR_TM_U_MID = 64, BR_TM_U_LO = 128, BR_TM_ACC = 192;
 struct BrSmem { int stage, op, bars, red, total; };
-__host__ __device__ inline BrSmem br_smem_layout() {
+struct BrMaps { CUtensorMap g, z, c, hs, h0; };
+
+// BR_NS = rows per sub-tile (UMMA N): 32, or 16 when the batch fits one wave of 32-row CTAs (shorter per-step chain,
+// twice as many SMs busy on small training batches).
+template <int BR_NS>
+struct BrK {
+static constexpr int BR_ROWS = BR_NS * BR_NT;
+static constexpr int RPT = BR_NS / 2, PAIRS = RPT / 2, NG = RPT / 8;    // rows / row pairs / 8-row groups per thread
+static constexpr int BR_ARR = BR_NS * BR_H * 4;                         // ring unit: one [NS][128] fp32 tile
+// The ring is counted in units; slot q (one sub-tile step: g | z | c | h_{t-1}) takes units (4q .. 4q+3) mod BR_RU.
+// 16-row sub-tiles: 24 units = 6 whole slots; 32-row sub-tiles: 11 units (2.75 slots) is what fits beside the
+// three operand tiles per sub-tile.
+static constexpr int BR_RU = BR_NS == 32 ? 11 : 24;
+static constexpr int BR_NB = (BR_RU + 3) / 4;                           // slot barriers (slots resident at once)
+static constexpr int BR_OPT = BR_NS * BR_H * 2;                         // one bf16 operand tile
+static constexpr int BR_TM_ACC_PER_TILE = 4 * BR_NS;
+static constexpr uint32_t BR_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BR_NS >> 3) << 17) | ((uint32_t)(BR_H >> 4) << 24);
+static constexpr uint32_t BR_KSTEP = (2 * (BR_NS >> 3) * 128) >> 4;
+
+static __host__ __device__ inline BrSmem br_smem_layout() {
   BrSmem L;
   L.stage = 0;
-  L.op = BR_STAGES * BR_STAGE;                  // [NT][hi|lo][BR_OPT]
-  L.bars = L.op + BR_NT * 2 * BR_OPT;
+  L.op = BR_RU * BR_ARR;                        // [NT][hi|mid|lo][BR_OPT]
+  L.bars = L.op + BR_NT * 3 * BR_OPT;
   L.red = L.bars + 16 * 8;                      // 32 floats of reduction scratch
   L.total = L.red + 32 * 4;
   return L;
 }
 
-struct BrMaps { CUtensorMap g, z, c, hs, h0; };
-
-__global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwdArgs a, const __grid_constant__ BrMaps maps, const int g_time_outer, const int hs_time_outer) {
+static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& maps, const int g_time_outer, const int hs_time_outer) {
   extern __shared__ __align__(128) unsigned char sm[];
   const BrSmem L = br_smem_layout();
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
@@ -321,12 +331,12 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * BR_ROWS;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  const int B_HREADY = 0, B_DFULL = 2, B_SFULL = 4, B_SEMPTY = 7;      // operand ready | accumulators ready | ring
+  const int B_HREADY = 0, B_DFULL = 2, B_SFULL = 4, B_SEMPTY = 4 + BR_NB;      // operand ready | accumulators ready | ring
 
   if (warp == BR_W_MMA) tmem_alloc(smem_u32(&tmem_base_s), 512);
   if (tid == 0) {
     for (int s = 0; s < BR_NT; ++s) { mbar_init(bar(B_HREADY + s), BR_EPI_WARPS / BR_NT); mbar_init(bar(B_DFULL + s), BR_MMA_WARPS); }
-    for (int st = 0; st < BR_STAGES; ++st) { mbar_init(bar(B_SFULL + st), 1); mbar_init(bar(B_SEMPTY + st), BR_EPI_WARPS / BR_NT); }
+    for (int st = 0; st < BR_NB; ++st) { mbar_init(bar(B_SFULL + st), 1); mbar_init(bar(B_SEMPTY + st), BR_EPI_WARPS / BR_NT); }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -347,28 +357,39 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
     for (int it = 0; it < d.T; ++it) {
 #pragma unroll
       for (int s = 0; s < BR_NT; ++s) {
-        const uint64_t dhi = dD0 + (uint64_t)(s * ((2 * BR_OPT) >> 4)), dlo = dhi + (BR_OPT >> 4);
+        const uint64_t dhi = dD0 + (uint64_t)(s * ((3 * BR_OPT) >> 4)), dmid = dhi + (BR_OPT >> 4), dlo = dmid + (BR_OPT >> 4);
         const uint32_t acc = tmem + BR_TM_ACC + s * BR_TM_ACC_PER_TILE;
-        mbar_wait(bar(B_HREADY + s), it & 1);          // dpre_t operand tile written, accumulators drained
+        mbar_wait(bar(B_HREADY + s), it & 1);          // dpre_t operand tiles written, accumulators drained
         tc_fence_after();
         if (leader) {
+          // six bf16 products of the three-term splits, 16 MMAs per issuing warp, grouped by magnitude so that the
+          // tensor core's accumulate truncation (2^-25 of the largest addend) stays relative to each group:
+          //   role 0 -> CA : U_mid.d_hi + U_hi.d_mid                     (2^-8)
+          //   role 1 -> CB : U_lo.d_hi + U_hi.d_lo                       (2^-16)
+          //   role 2 -> M1 / M2 : U_hi.d_hi + U_mid.d_mid, k-steps 0..3 / 4..7
           if (role == 0) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_ts1(acc, tmem + BR_TM_U_LO + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
-              umma_ts1(acc, tmem + BR_TM_U_HI + ks * 8, dlo + ks * BR_KSTEP, BR_IDESC, 1);
+            for (int ks = 0; ks < 8; ++ks) {
+              umma_ts1(acc, tmem + BR_TM_U_MID + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
+              umma_ts1(acc, tmem + BR_TM_U_HI + ks * 8, dmid + ks * BR_KSTEP, BR_IDESC, 1);
             }
           } else if (role == 1) {
 #pragma unroll
-            for (int ks = 4; ks < 8; ++ks) {
-              umma_ts1(acc + BR_NS, tmem + BR_TM_U_LO + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 4);
+            for (int ks = 0; ks < 8; ++ks) {
+              umma_ts1(acc + BR_NS, tmem + BR_TM_U_LO + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
               umma_ts1(acc + BR_NS, tmem + BR_TM_U_HI + ks * 8, dlo + ks * BR_KSTEP, BR_IDESC, 1);
             }
           } else {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_ts1(acc + 2 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ts1(acc + 2 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 0);
+              umma_ts1(acc + 2 * BR_NS, tmem + BR_TM_U_MID + ks * 8, dmid + ks * BR_KSTEP, BR_IDESC, 1);
+            }
 #pragma unroll
-            for (int ks = 4; ks < 8; ++ks) umma_ts1(acc + 3 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 4);
+            for (int ks = 4; ks < 8; ++ks) {
+              umma_ts1(acc + 3 * BR_NS, tmem + BR_TM_U_HI + ks * 8, dhi + ks * BR_KSTEP, BR_IDESC, ks > 4);
+              umma_ts1(acc + 3 * BR_NS, tmem + BR_TM_U_MID + ks * 8, dmid + ks * BR_KSTEP, BR_IDESC, 1);
+            }
           }
           umma_commit1(bar(B_DFULL + s));
         }
@@ -385,19 +406,23 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
       for (int it = 0; it < d.T; ++it) {
         const int t = d.T - 1 - it;
         for (int s = 0; s < BR_NT; ++s) {
-          const int q = it * BR_NT + s, st = q % BR_STAGES;
+          const int q = it * BR_NT + s;
           const int first = row0 + s * BR_NS;
           const bool with_hp = !(t == 0 && hp_zero_at_t0);
-          if (q >= BR_STAGES) mbar_wait(bar(B_SEMPTY + st), ((q / BR_STAGES) - 1) & 1);
-          const uint32_t fb = bar(B_SFULL + st), dst = smem_u32(sm + L.stage + st * BR_STAGE);
+          // the units of slot q were last used by slots (4q - RU)/4 and (4q + 3 - RU)/4: both must be consumed
+          if (4 * q >= BR_RU) { const int qa = (4 * q - BR_RU) / 4; mbar_wait(bar(B_SEMPTY + qa % BR_NB), (qa / BR_NB) & 1); }
+          if (4 * q + 3 >= BR_RU && (BR_RU & 3)) { const int qb = (4 * q + 3 - BR_RU) / 4; mbar_wait(bar(B_SEMPTY + qb % BR_NB), (qb / BR_NB) & 1); }
+          const uint32_t fb = bar(B_SFULL + q % BR_NB), ring = smem_u32(sm + L.stage);
+          const int u0 = (4 * q) % BR_RU;
+          auto unit = [&](int k) { return ring + (uint32_t)(((u0 + k) % BR_RU) * BR_ARR); };
           mbar_expect_tx(fb, (uint32_t)BR_ARR * (with_hp ? 4u : 3u));
-          if (g_time_outer) tma_load_3d(dst, &maps.g, 0, first, t, fb); else tma_load_3d(dst, &maps.g, 0, t, first, fb);
-          tma_load_3d(dst + BR_ARR, &maps.z, 0, first, t, fb);
-          tma_load_3d(dst + 2 * BR_ARR, &maps.c, 0, first, t, fb);
+          if (g_time_outer) tma_load_3d(unit(0), &maps.g, 0, first, t, fb); else tma_load_3d(unit(0), &maps.g, 0, t, first, fb);
+          tma_load_3d(unit(1), &maps.z, 0, first, t, fb);
+          tma_load_3d(unit(2), &maps.c, 0, first, t, fb);
           if (t > 0) {
-            if (hs_time_outer) tma_load_3d(dst + 3 * BR_ARR, &maps.hs, 0, first, t - 1, fb); else tma_load_3d(dst + 3 * BR_ARR, &maps.hs, 0, t - 1, first, fb);
+            if (hs_time_outer) tma_load_3d(unit(3), &maps.hs, 0, first, t - 1, fb); else tma_load_3d(unit(3), &maps.hs, 0, t - 1, first, fb);
           } else if (with_hp) {
-            tma_load_3d(dst + 3 * BR_ARR, &maps.h0, 0, first, 0, fb);
+            tma_load_3d(unit(3), &maps.h0, 0, first, 0, fb);
           }
         }
       }
@@ -421,10 +446,11 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t hi[8], lo[8];
+        uint32_t hi[8], mid[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split2_bf16(uv[c * 16 + 2 * j], uv[c * 16 + 2 * j + 1], hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) split3_bf16(uv[c * 16 + 2 * j], uv[c * 16 + 2 * j + 1], hi[j], mid[j], lo[j]);
         tmem_st8(tmem + lane_base + BR_TM_U_HI + part * 16 + c * 8, hi);
+        tmem_st8(tmem + lane_base + BR_TM_U_MID + part * 16 + c * 8, mid);
         tmem_st8(tmem + lane_base + BR_TM_U_LO + part * 16 + c * 8, lo);
       }
       tmem_st_wait();
@@ -434,26 +460,26 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
 
     const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
     const float2 sz2 = make_float2(sz, sz), sn2 = make_float2(sn, sn), msz2 = make_float2(-sz, -sz), one2 = make_float2(1.f, 1.f);
-    const int first_row = row0 + es * BR_NS + rh * 16;
+    const int first_row = row0 + es * BR_NS + rh * RPT;
     const int rows_left = d.B - first_row;
-    unsigned char* hop = sm + L.op + es * (2 * BR_OPT) + (n >> 3) * ((BR_NS >> 3) * 128) + (rh * 2) * 128 + (n & 7) * 16;
-    const uint32_t acc = tmem + lane_base + BR_TM_ACC + es * BR_TM_ACC_PER_TILE + rh * 16;
+    unsigned char* hop = sm + L.op + es * (3 * BR_OPT) + (n >> 3) * ((BR_NS >> 3) * 128) + (rh * NG) * 128 + (n & 7) * 16;
+    const uint32_t acc = tmem + lane_base + BR_TM_ACC + es * BR_TM_ACC_PER_TILE + rh * RPT;
     float* dpre_p = a.dpre_ws + (size_t)first_row * BR_H + n;             // + t*B*H per step
-    float2 carry[8];                                                       // z G of the previous (later) step
+    float2 carry[PAIRS];                                                       // z G of the previous (later) step
 #pragma unroll
-    for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < PAIRS; ++q) carry[q] = make_float2(0.f, 0.f);
     float2 db_u = make_float2(0.f, 0.f), db_g = db_u, dze = db_u, dnu = db_u;
 
     for (int it = 0; it <= d.T; ++it) {
       const int t = d.T - 1 - it;
-      float2 G[8];
+      float2 G[PAIRS];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) G[q] = carry[q];
+      for (int q = 0; q < PAIRS; ++q) G[q] = carry[q];
       if (it > 0) {                                     // delta += dpre_{t+1} . U^T
         mbar_wait(bar(B_DFULL + es), (it - 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < NG; ++g) {
           float va[8], vb[8], v1[8], v2[8];
           tmem_ld8(acc + g * 8, va);
           tmem_ld8(acc + BR_NS + g * 8, vb);
@@ -471,24 +497,29 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
       if (it == d.T) {                                  // delta after t = 0 is d h0
         if (a.d_h0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
+          for (int j = 0; j < RPT; ++j)
             if (j < rows_left) a.d_h0[(size_t)(first_row + j) * BR_H + n] = (j & 1) ? G[j >> 1].y : G[j >> 1].x;
         }
         break;
       }
-      const int qi = it * BR_NT + es, st = qi % BR_STAGES;
-      mbar_wait_poll(bar(B_SFULL + st), (qi / BR_STAGES) & 1);
-      const float* tile = reinterpret_cast<const float*>(sm + L.stage + st * BR_STAGE) + (rh * 16) * BR_H + n;
+      const int qi = it * BR_NT + es, sb = qi % BR_NB;
+      mbar_wait_poll(bar(B_SFULL + sb), (qi / BR_NB) & 1);
+      const int u0 = (4 * qi) % BR_RU;
+      const float* ring = reinterpret_cast<const float*>(sm + L.stage) + (rh * RPT) * BR_H + n;
+      const float* tg = ring + u0 * (BR_ARR / 4);
+      const float* tz = ring + ((u0 + 1) % BR_RU) * (BR_ARR / 4);
+      const float* tcc = ring + ((u0 + 2) % BR_RU) * (BR_ARR / 4);
+      const float* th = ring + ((u0 + 3) % BR_RU) * (BR_ARR / 4);
       const bool hp_zero = t == 0 && hp_zero_at_t0;
-      uint32_t hi[8], lo[8];
-      float2 dp[8];
+      uint32_t hi[PAIRS], mid[PAIRS], lo[PAIRS];
+      float2 dp[PAIRS];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float* e0 = tile + (2 * q) * BR_H;
-        const float2 g = make_float2(e0[0], e0[BR_H]);
-        const float2 z = make_float2(e0[BR_ARR / 4], e0[BR_ARR / 4 + BR_H]);
-        const float2 c = make_float2(e0[2 * (BR_ARR / 4)], e0[2 * (BR_ARR / 4) + BR_H]);
-        const float2 hp = hp_zero ? make_float2(0.f, 0.f) : make_float2(e0[3 * (BR_ARR / 4)], e0[3 * (BR_ARR / 4) + BR_H]);
+      for (int q = 0; q < PAIRS; ++q) {
+        const int e = (2 * q) * BR_H;
+        const float2 g = make_float2(tg[e], tg[e + BR_H]);
+        const float2 z = make_float2(tz[e], tz[e + BR_H]);
+        const float2 c = make_float2(tcc[e], tcc[e + BR_H]);
+        const float2 hp = hp_zero ? make_float2(0.f, 0.f) : make_float2(th[e], th[e + BR_H]);
         const float2 Gq = __fadd2_rn(G[q], g);
         const float2 w = __fadd2_rn(one2, make_float2(-z.x, -z.y));                       // 1 - z
         const float2 cG = __fmul2_rn(c, Gq);
@@ -501,19 +532,21 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
         db_u = __fadd2_rn(db_u, dc); db_g = __fadd2_rn(db_g, dz);
         dze = __ffma2_rn(w, cG, dze);                                                      // cu:116 (sigmoid' applied at the end)
         dnu = __fadd2_rn(dnu, cG);                                                         // cu:117
-        split2_bf16(dp[q].x, dp[q].y, hi[q], lo[q]);
+        split3_bf16(dp[q].x, dp[q].y, hi[q], mid[q], lo[q]);
       }
-      *reinterpret_cast<uint4*>(hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(hop + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      *reinterpret_cast<uint4*>(hop + BR_OPT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(hop + BR_OPT + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        *reinterpret_cast<uint4*>(hop + g * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+        *reinterpret_cast<uint4*>(hop + BR_OPT + g * 128) = make_uint4(mid[4 * g], mid[4 * g + 1], mid[4 * g + 2], mid[4 * g + 3]);
+        *reinterpret_cast<uint4*>(hop + 2 * BR_OPT + g * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(B_HREADY + es)); mbar_arrive(bar(B_SEMPTY + st)); }
+      if (lane == 0) { mbar_arrive(bar(B_HREADY + es)); mbar_arrive(bar(B_SEMPTY + sb)); }
       float* dst = dpre_p + (size_t)t * d.B * BR_H;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < PAIRS; ++q) {
         if (2 * q < rows_left) dst[(2 * q) * BR_H] = dp[q].x;
         if (2 * q + 1 < rows_left) dst[(2 * q + 1) * BR_H] = dp[q].y;
       }
@@ -547,15 +580,28 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
   __syncthreads();
   if (warp == BR_W_MMA) tmem_dealloc(tmem, 512);
 }
+};   // struct BrK
+
+template <int NS>
+__global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwdArgs a, const __grid_constant__ BrMaps maps, const int g_time_outer, const int hs_time_outer) {
+  BrK<NS>::run(a, maps, g_time_outer, hs_time_outer);
+}
 
 bool tc_bwd_rec_supports(const Dims& d) {
   return d.rW == 0 && d.rU == 0 && d.H == BR_H && d.gate_nl == FGRNN_NL_SIGMOID && d.update_nl == FGRNN_NL_TANH;
 }
-int tc_bwd_rec_ctas(const Dims& d) { return (d.B + BR_ROWS - 1) / BR_ROWS; }
+// 16-row sub-tiles while the batch fits one wave of 32-row CTAs; FGRNN_TC_BR_NS=16|32 overrides (tests, benchmarks)
+static int br_ns_for(int B) {
+  int ns = B <= 148 * 32 ? 16 : 32;
+  if (const char* e = getenv("FGRNN_TC_BR_NS")) { if (atoi(e) == 16) ns = 16; else if (atoi(e) == 32) ns = 32; }
+  return ns;
+}
+int tc_bwd_rec_ctas(const Dims& d) { const int rows = br_ns_for(d.B) * BR_NT; return (d.B + rows - 1) / rows; }
 
-int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream) {
+template <int BR_NS>
+static int launch_tc_bwd_rec_ns(const SmemBwdArgs& a, cudaStream_t stream) {
+  using K = BrK<BR_NS>;
   const Dims& d = a.d;
-  if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
   BrMaps maps;
   int g_to = 0, hs_to = 0, dummy = 0, rc;
   if ((rc = make_row_tile_map(&maps.g, a.grad_h, false, BR_H, d.B, d.T, a.gsb, a.gst, BR_NS, &g_to))) return rc;
@@ -566,11 +612,16 @@ int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream) {
   if ((rc = make_row_tile_map(&maps.hs, hs, false, BR_H, d.B, d.T, a.hs ? a.hsb : BR_H, a.hs ? a.hst : (int64_t)d.B * BR_H, BR_NS, &hs_to))) return rc;
   const float* h0 = a.h0 ? a.h0 : a.z_s;
   if ((rc = make_row_tile_map(&maps.h0, h0, false, BR_H, d.B, 1, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
-  const BrSmem L = br_smem_layout();
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_bwd_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  tc_bwd_rec_kernel<<<tc_bwd_rec_ctas(d), BR_THREADS, L.total, stream>>>(a, maps, g_to, hs_to);
+  const BrSmem L = K::br_smem_layout();
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_bwd_rec_kernel<BR_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  tc_bwd_rec_kernel<BR_NS><<<(d.B + K::BR_ROWS - 1) / K::BR_ROWS, BR_THREADS, L.total, stream>>>(a, maps, g_to, hs_to);
   FGRNN_LAUNCH_CHECK("tc_bwd_rec_kernel");
   return FGRNN_OK;
+}
+
+int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream) {
+  if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
+  return br_ns_for(a.d.B) == 16 ? launch_tc_bwd_rec_ns<16>(a, stream) : launch_tc_bwd_rec_ns<32>(a, stream);
 }
 
 }  // namespace fgrnn

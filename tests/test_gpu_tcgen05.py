@@ -137,6 +137,15 @@ def test_tcgen05_backward_against_autograd(B, T, I, layout, h0_given, bf):
     assert all(torch.equal(g[k], g2[k]) for k in ("W", "U", "bias_gate", "zeta"))
 
 
+@pytest.mark.parametrize("ns", ["16", "32"])
+def test_tcgen05_backward_both_sub_tile_widths(monkeypatch, ns):
+    """The reverse recurrence takes 16-row sub-tiles while the batch fits one wave of 32-row CTAs and 32-row ones
+    beyond; FGRNN_TC_BR_NS pins the width (the per-CTA partial rows follow it)."""
+    monkeypatch.setenv("FGRNN_TC_BR_NS", ns)
+    test_tcgen05_backward_against_autograd(77, 9, 32, "HI", True, True)
+    test_tcgen05_backward_against_autograd(130, 7, 16, "IH", False, False)
+
+
 def test_training_step_replays_from_a_cuda_graph():
     """The C-ABI calls are capture-safe (no allocation, no host sync, tensor maps baked into the kernel
     parameters): a captured forward + BPTT + SGD step updates the weights exactly like the eager step."""
