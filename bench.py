@@ -337,6 +337,11 @@ def main():
     clocks = sampler.stop() if sampler else None
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    rank_ms = [total_ms / args.steps]
+    if world > 1:                                 # per-rank step times (diagnostic; the headline uses the max)
+        tl = [torch.zeros(1, device=device) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([total_ms / args.steps], device=device))
+        rank_ms = [float(t) for t in tl]
     total_ms = sharding.max_over_ranks(total_ms, device)
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms * 1e-3)
@@ -409,7 +414,7 @@ def main():
         line = {
             "metric": "FastGRNN sequences/sec (%s)" % ("fwd+bwd train" if train else "fwd infer"),
             "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "rank_ms_per_step": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload, "per_gpu_batch": B, "global_batch": B * world,
                        "T": T, "input": I, "hidden": H, "wRank": w["wR"], "uRank": w["uR"], "x_dtype": w["x"],

@@ -80,7 +80,8 @@ enum { FGRNN_F32 = 0, FGRNN_BF16 = 1 };
 enum {
   FGRNN_PATH_GENERIC = 0,    /* any shape: weights streamed through L1/L2 */
   FGRNN_PATH_SMEM = 1,       /* persistent FFMA kernel, weights resident in shared memory */
-  FGRNN_PATH_TCGEN05 = 2     /* tcgen05/TMEM kernel */
+  FGRNN_PATH_TCGEN05 = 2,    /* tcgen05/TMEM kernel */
+  FGRNN_PATH_LOWRANK = 3     /* forward only: persistent FFMA kernel for W1.W2 / U1.U2 with H = 256 (backward: generic) */
 };
 
 /* Problem description shared by forward and backward. */

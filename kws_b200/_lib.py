@@ -19,8 +19,8 @@ NL = {"sigmoid": 0, "relu": 1, "tanh": 2, "quantTanh": 3, "quantSigm": 4, "quant
 NL_NAMES = {v: k for k, v in NL.items()}
 LAYOUT_IH, LAYOUT_HI = 0, 1
 F32, BF16 = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_SMEM, PATH_TCGEN05 = -1, 0, 1, 2
-PATH_NAMES = {0: "generic", 1: "smem", 2: "tcgen05"}
+PATH_AUTO, PATH_GENERIC, PATH_SMEM, PATH_TCGEN05, PATH_LOWRANK = -1, 0, 1, 2, 3
+PATH_NAMES = {0: "generic", 1: "smem", 2: "tcgen05", 3: "lowrank"}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfastgrnn_b200.so")

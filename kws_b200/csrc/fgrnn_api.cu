@@ -48,7 +48,7 @@ int validate_problem(const FgrnnProblem& p) {
   if (p.weight_layout != FGRNN_LAYOUT_IH && p.weight_layout != FGRNN_LAYOUT_HI)
     return fail(FGRNN_ERR_ENUM, "weight_layout=%d unknown", p.weight_layout);
   if (p.x_dtype != FGRNN_F32 && p.x_dtype != FGRNN_BF16) return fail(FGRNN_ERR_ENUM, "x_dtype=%d unknown", p.x_dtype);
-  if (p.force_path < -1 || p.force_path > FGRNN_PATH_TCGEN05) return fail(FGRNN_ERR_ENUM, "force_path=%d unknown", p.force_path);
+  if (p.force_path < -1 || p.force_path > FGRNN_PATH_LOWRANK) return fail(FGRNN_ERR_ENUM, "force_path=%d unknown", p.force_path);
   if (p.rW == 0 && !p.W) return fail(FGRNN_ERR_NULL, "W must be a CUDA tensor (NULL with wRank == 0)");
   if (p.rW > 0 && (!p.W1 || !p.W2)) return fail(FGRNN_ERR_NULL, "W1/W2 must be CUDA tensors (NULL with wRank > 0)");
   if (p.rU == 0 && !p.U) return fail(FGRNN_ERR_NULL, "U must be a CUDA tensor (NULL with uRank == 0)");
@@ -112,9 +112,21 @@ bool tc_fwd_ok(const FgrnnForward& f) {
          tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T);
 }
 
+// low-rank FFMA family: 16-byte vector access on x, h0 and every output; weights are copied from their canonical form
+bool lr_fwd_ok(const FgrnnForward& f) {
+  const FgrnnProblem& p = f.p;
+  if (!lr_path_supports(dims_of(p))) return false;
+  const bool xok = p.x_dtype == FGRNN_BF16 ? (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 : aligned16(p.x);
+  return xok && mult4(p.x_stride_b) && mult4(p.x_stride_t) && aligned16(p.W1) && aligned16(p.W2) && aligned16(p.U1) &&
+         aligned16(p.U2) && aligned16(p.bias_gate) && aligned16(p.bias_update) && aligned16(p.h0) && aligned16(f.out) &&
+         mult4(f.out_stride_b) && mult4(f.out_stride_t) && aligned16(f.h_last) && aligned16(f.save_z) &&
+         aligned16(f.save_c) && (!f.save_z == !f.save_c);
+}
+
 int select_fwd_path(const FgrnnForward& f) {
   if (f.p.force_path >= 0) return f.p.force_path;
-  if (tc_fwd_ok(f)) return FGRNN_PATH_TCGEN05;       // 5x the FFMA family at C2, faster per step even for one CTA
+  if (tc_fwd_ok(f)) return FGRNN_PATH_TCGEN05;
+  if (lr_fwd_ok(f)) return FGRNN_PATH_LOWRANK;       // 5x the FFMA family at C2, faster per step even for one CTA
   return smem_fwd_ok(f) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
 }
 
@@ -123,7 +135,7 @@ FwdPlan plan_forward(const FgrnnForward& f, void* ws) {
   FwdPlan pl{};
   pl.path = select_fwd_path(f);
   Carver cv(ws);
-  if (p.weight_layout == FGRNN_LAYOUT_HI && pl.path == FGRNN_PATH_GENERIC) {
+  if (p.weight_layout == FGRNN_LAYOUT_HI && (pl.path == FGRNN_PATH_GENERIC || pl.path == FGRNN_PATH_LOWRANK)) {
     if (p.rW == 0) pl.Wc = cv.take<float>((size_t)p.I * p.H);
     else { pl.W1c = cv.take<float>((size_t)p.I * p.rW); pl.W2c = cv.take<float>((size_t)p.rW * p.H); }
     if (p.rU == 0) pl.Uc = cv.take<float>((size_t)p.H * p.H);
@@ -140,6 +152,8 @@ int validate_forward(const FgrnnForward& f) {
   const int path = select_fwd_path(f);
   if (path == FGRNN_PATH_SMEM && !smem_fwd_ok(f))
     return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
+  if (path == FGRNN_PATH_LOWRANK && !lr_fwd_ok(f))
+    return fail(FGRNN_ERR_SHAPE, "forced low-rank path needs H=256, wRank%%4==0 (<=32), uRank%%4==0 (<=64), I%%4==0 (<=64) and 16-byte aligned tensors");
   if (path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f))
     return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, I%%8==0, I<=64, sigmoid gate / tanh update, 16-byte aligned tensors and strides");
   return FGRNN_OK;
@@ -186,6 +200,7 @@ bool tc_bwd_ok(const FgrnnBackward& g) {
 }
 
 int select_bwd_path(const FgrnnBackward& g) {
+  if (g.p.force_path == FGRNN_PATH_LOWRANK) return FGRNN_PATH_GENERIC;      // forward-only family
   if (g.p.force_path >= 0) return g.p.force_path;
   if (tc_bwd_ok(g)) return FGRNN_PATH_TCGEN05;
   return smem_bwd_ok(g) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
@@ -370,7 +385,7 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     if (rc) return rc;
     a.Wc = pl.Wc; a.Uc = pl.Uc; a.W1c = pl.W1c; a.W2c = pl.W2c; a.U1c = pl.U1c; a.U2c = pl.U2c;
   }
-  return launch_gen_fwd(a, stream);
+  return pl.path == FGRNN_PATH_LOWRANK ? launch_lr_fwd(a, stream) : launch_gen_fwd(a, stream);
 }
 
 int fgrnn_backward(const FgrnnBackward* g, void* stream_) {

@@ -18,6 +18,10 @@ struct FwdArgs {
 
 int launch_gen_fwd(const FwdArgs& a, cudaStream_t stream);
 
+// low-rank persistent FFMA forward (fgrnn_lr.cu): H = 256, W1/W2/U1/U2 resident in shared memory
+bool lr_path_supports(const Dims& d);
+int launch_lr_fwd(const FwdArgs& a, cudaStream_t stream);
+
 // ---- backward, serial part ---------------------------------------------------------------
 struct BwdRecArgs {
   Dims d;

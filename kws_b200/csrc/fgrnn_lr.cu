@@ -1,0 +1,236 @@
+// Low-rank forward recurrence (rnn.py:280-287, factored order (x.W1).W2 + (h.U1).U2), hidden size 256:
+// persistent FFMA kernel with W1, W2, U1, U2 resident in shared memory for all T steps.
+//
+//   CTA = 64 batch rows, 512 threads.  Per step:
+//   stage 1  s[row][j] = h[row][:] . U1[:][j]  (j < rU)   and   sx[row][j] = x_t[row][:] . W1[:][j]  (j < rW)
+//            thread tile 4 rows x 4 ranks, K in blocks of 4: 8 LDS.128 per 64 FFMA.  The h.U1 part (K = 256) runs on
+//            the first 4*rU threads (for rU = 32: warps 0-3, one per scheduler), the x.W1 part (K = I) beside it.
+//   stage 2  pre[row][n] = [s | sx][row][:] . [U2 ; W2][:][n]
+//            thread tile 8 rows x 4 units (s broadcast within the warp, weights 16 B per lane): 12 LDS.128 per 128 FFMA,
+//            followed by the gate update on the thread's 32 elements, h back to shared memory, 16-byte global stores.
+// Algorithmic FLOPs per row-step 2*(256*32 + 32*16 + 48*256) = 41 984; the kernel is FFMA-issue bound.
+// The tensor-core version of this path (two chained tcgen05 stages) is the round-2 item in DESIGN.md section 6.
+#include "fgrnn_kernels.cuh"
+
+namespace fgrnn {
+
+constexpr int LR_H = 256, LR_BM = 64, LR_THREADS = 512;
+constexpr int LR_HP = LR_H + 4;                 // padded h row: the 4 rows of a stage-1 tile fall into distinct banks
+constexpr int LR_MAX_X4 = 2;                    // x tile: at most 64 x 64 floats = 1024 float4, two per thread
+
+struct LrSmem { int U1, W1, V2, h, s, x, total, SP; };      // offsets in floats
+__host__ __device__ inline LrSmem lr_smem_layout(int I, int rW, int rU) {
+  LrSmem L;
+  L.SP = rU + rW + 4;
+  L.U1 = 0;
+  L.W1 = L.U1 + LR_H * rU;
+  L.V2 = L.W1 + I * rW;                         // [rU + rW][H]: U2 stacked on W2
+  L.h = L.V2 + (rU + rW) * LR_H;
+  L.s = L.h + LR_BM * LR_HP;
+  L.x = L.s + LR_BM * L.SP;                     // [2][BM][I]
+  L.total = L.x + 2 * LR_BM * I;
+  return L;
+}
+
+__device__ __forceinline__ void lr_copy4(float* dst, const float* __restrict__ src, int n, int tid) {
+  for (int i = tid; i < n / 4; i += LR_THREADS) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+}
+
+__device__ __forceinline__ void lr_fma4(float (&acc)[4], float s, const float4& w) {
+  acc[0] = fmaf(s, w.x, acc[0]); acc[1] = fmaf(s, w.y, acc[1]); acc[2] = fmaf(s, w.z, acc[2]); acc[3] = fmaf(s, w.w, acc[3]);
+}
+
+// 4 rows x 4 outputs over K (multiple of 4): A rows in shared memory (stride lda), weights [K][ldw] in shared memory
+template <int UNROLL>
+__device__ __forceinline__ void lr_tile_4x4(float (&acc)[4][4], const float* A, int lda, const float* Wt, int ldw, int K) {
+#pragma unroll UNROLL
+  for (int k = 0; k < K; k += 4) {
+    float4 av[4], wv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) av[r] = *reinterpret_cast<const float4*>(A + r * lda + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) wv[kk] = *reinterpret_cast<const float4*>(Wt + (k + kk) * ldw);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      lr_fma4(acc[r], av[r].x, wv[0]); lr_fma4(acc[r], av[r].y, wv[1]);
+      lr_fma4(acc[r], av[r].z, wv[2]); lr_fma4(acc[r], av[r].w, wv[3]);
+    }
+  }
+}
+
+template <bool FAST_NL>
+__global__ void __launch_bounds__(LR_THREADS, 1) lr_fwd_kernel(const FwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const Dims d = a.d;
+  const int I = d.I, rW = d.rW, rU = d.rU, R = rU + rW;
+  const LrSmem L = lr_smem_layout(I, rW, rU);
+  float *U1s = sm + L.U1, *W1s = sm + L.W1, *V2s = sm + L.V2, *h_s = sm + L.h, *s_s = sm + L.s, *x_s = sm + L.x;
+  const int SP = L.SP;
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * LR_BM;
+
+  // ---- prologue: weights, h0, x_0 -----------------------------------------------------------
+  lr_copy4(U1s, a.U1c, LR_H * rU, tid);
+  lr_copy4(W1s, a.W1c, I * rW, tid);
+  lr_copy4(V2s, a.U2c, rU * LR_H, tid);
+  lr_copy4(V2s + rU * LR_H, a.W2c, rW * LR_H, tid);
+  for (int i = tid; i < LR_BM * (LR_H / 4); i += LR_THREADS) {
+    const int r = i / (LR_H / 4), c4 = i - r * (LR_H / 4);
+    const int row = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.h0 != nullptr && row < d.B) v = __ldg(reinterpret_cast<const float4*>(a.h0 + (size_t)row * LR_H) + c4);
+    *reinterpret_cast<float4*>(h_s + r * LR_HP + c4 * 4) = v;
+  }
+  // x tile tasks of this thread: (row, 4-feature chunk), step invariant
+  const int xq = I / 4, xtasks = LR_BM * xq;
+  int x_dst[LR_MAX_X4];
+  int64_t x_src[LR_MAX_X4];
+  bool x_live[LR_MAX_X4];
+#pragma unroll
+  for (int q = 0; q < LR_MAX_X4; ++q) {
+    const int e = q * LR_THREADS + tid;
+    const int r = e / xq, c4 = e - r * xq;
+    x_live[q] = e < xtasks && row0 + r < d.B;
+    x_dst[q] = e < xtasks ? r * I + c4 * 4 : -1;
+    x_src[q] = (int64_t)(row0 + r) * a.xsb + c4 * 4;
+  }
+  auto load_x4 = [&](int q, int t) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x_live[q]) {
+      const int64_t idx = x_src[q] + (int64_t)t * a.xst;
+      if (d.x_dtype == FGRNN_BF16) {
+        const uint2 p = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.x) + idx));
+        v.x = __uint_as_float(p.x << 16); v.y = __uint_as_float(p.x & 0xffff0000u);
+        v.z = __uint_as_float(p.y << 16); v.w = __uint_as_float(p.y & 0xffff0000u);
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + idx));
+      }
+    }
+    return v;
+  };
+#pragma unroll
+  for (int q = 0; q < LR_MAX_X4; ++q)
+    if (x_dst[q] >= 0) *reinterpret_cast<float4*>(x_s + x_dst[q]) = load_x4(q, 0);
+
+  // stage-1 roles
+  const int ujg = rU / 4, wjg = rW / 4;
+  const int nU = 16 * ujg, nUpad = (nU + 31) & ~31, nW = 16 * wjg;
+  const bool is_u = tid < nU, is_w = tid >= nUpad && tid < nUpad + nW;
+  const int t1 = is_u ? tid : tid - nUpad;
+  const int s1_jg = is_u ? t1 % ujg : (is_w ? t1 % wjg : 0);
+  const int s1_rg = is_u ? t1 / ujg : (is_w ? t1 / wjg : 0);
+  // stage-2 / epilogue roles
+  const int ng = tid & 63, rg = tid >> 6, n0 = ng * 4;
+  const float4 bg = __ldg(reinterpret_cast<const float4*>(a.bias_gate) + ng);
+  const float4 bu = __ldg(reinterpret_cast<const float4*>(a.bias_update) + ng);
+  const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
+  const int first_row = row0 + rg * 8;
+  float* outp = a.out ? a.out + (size_t)first_row * a.osb + n0 : nullptr;
+  float* zp = a.save_z ? a.save_z + (size_t)first_row * LR_H + n0 : nullptr;
+  float* cp = a.save_c ? a.save_c + (size_t)first_row * LR_H + n0 : nullptr;
+  const int rows_left = d.B - first_row;
+  __syncthreads();
+
+  for (int t = 0; t < d.T; ++t) {
+    const float* xc = x_s + (t & 1) * LR_BM * I;
+    float* xn = x_s + ((t & 1) ^ 1) * LR_BM * I;
+    float4 xnext[LR_MAX_X4];
+    const bool more = t + 1 < d.T;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < LR_MAX_X4; ++q) xnext[q] = load_x4(q, t + 1);        // lands during the two stages
+    }
+    // ---- stage 1 ----
+    if (is_u) {
+      float acc[4][4] = {};
+      lr_tile_4x4<2>(acc, h_s + (s1_rg * 4) * LR_HP, LR_HP, U1s + s1_jg * 4, rU, LR_H);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4*>(s_s + (s1_rg * 4 + r) * SP + s1_jg * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    } else if (is_w) {
+      float acc[4][4] = {};
+      lr_tile_4x4<1>(acc, xc + (s1_rg * 4) * I, I, W1s + s1_jg * 4, rW, I);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4*>(s_s + (s1_rg * 4 + r) * SP + rU + s1_jg * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    // ---- stage 2: 8 rows x 4 units ----
+    float acc[8][4] = {};
+    {
+      const float* sp = s_s + (rg * 8) * SP;
+      const float* vp = V2s + n0;
+#pragma unroll 1
+      for (int j = 0; j < R; j += 4) {
+        float4 vv[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) vv[jj] = *reinterpret_cast<const float4*>(vp + (j + jj) * LR_H);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 sv = *reinterpret_cast<const float4*>(sp + r * SP + j);
+          lr_fma4(acc[r], sv.x, vv[0]); lr_fma4(acc[r], sv.y, vv[1]); lr_fma4(acc[r], sv.z, vv[2]); lr_fma4(acc[r], sv.w, vv[3]);
+        }
+      }
+    }
+    // ---- gate update (rnn.py:289-295) ----
+    const bool last = t == d.T - 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float* hrow = h_s + (rg * 8 + r) * LR_HP + n0;
+      const float4 ho = *reinterpret_cast<const float4*>(hrow);
+      const float hold[4] = {ho.x, ho.y, ho.z, ho.w};
+      const float bgv[4] = {bg.x, bg.y, bg.z, bg.w}, buv[4] = {bu.x, bu.y, bu.z, bu.w};
+      float hn[4], zv[4], cv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float pre = acc[r][c];
+        zv[c] = FAST_NL ? sigmoid_fast(pre + bgv[c]) : act_rt(d.gate_nl, pre + bgv[c]);
+        cv[c] = FAST_NL ? tanh_fast(pre + buv[c]) : act_rt(d.update_nl, pre + buv[c]);
+        hn[c] = fmaf(zv[c], hold[c], (fmaf(sz, 1.0f - zv[c], sn)) * cv[c]);
+      }
+      *reinterpret_cast<float4*>(hrow) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      if (r < rows_left) {
+        if (outp) *reinterpret_cast<float4*>(outp + (size_t)r * a.osb) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        if (zp) {
+          *reinterpret_cast<float4*>(zp + (size_t)r * LR_H) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+          *reinterpret_cast<float4*>(cp + (size_t)r * LR_H) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+        if (last && a.h_last) *reinterpret_cast<float4*>(a.h_last + (size_t)(first_row + r) * LR_H + n0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      }
+    }
+    if (outp) outp += a.ost;
+    if (zp) { zp += (size_t)d.B * LR_H; cp += (size_t)d.B * LR_H; }
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < LR_MAX_X4; ++q)
+        if (x_dst[q] >= 0) *reinterpret_cast<float4*>(xn + x_dst[q]) = xnext[q];
+    }
+    __syncthreads();
+  }
+}
+
+size_t lr_fwd_smem_bytes(const Dims& d) { return sizeof(float) * (size_t)lr_smem_layout(d.I, d.rW, d.rU).total; }
+
+bool lr_path_supports(const Dims& d) {
+  if (d.H != LR_H || d.rW <= 0 || d.rU <= 0) return false;
+  if (d.rW % 4 || d.rU % 4 || d.I % 4 || d.I < 4 || d.I > 64 || d.rW > 32 || d.rU > 64) return false;
+  return lr_fwd_smem_bytes(d) <= 227 * 1024;
+}
+
+int launch_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
+  if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
+  const size_t smem = lr_fwd_smem_bytes(a.d);
+  const bool fast = a.d.gate_nl == FGRNN_NL_SIGMOID && a.d.update_nl == FGRNN_NL_TANH;
+  const unsigned grid = (unsigned)((a.d.B + LR_BM - 1) / LR_BM);
+  if (fast) {
+    FGRNN_CUDA_TRY(cudaFuncSetAttribute(lr_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lr_fwd_kernel<true><<<grid, LR_THREADS, smem, stream>>>(a);
+  } else {
+    FGRNN_CUDA_TRY(cudaFuncSetAttribute(lr_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lr_fwd_kernel<false><<<grid, LR_THREADS, smem, stream>>>(a);
+  }
+  FGRNN_LAUNCH_CHECK("lr_fwd_kernel");
+  return FGRNN_OK;
+}
+
+}  // namespace fgrnn

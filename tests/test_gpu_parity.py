@@ -345,3 +345,40 @@ def test_auto_plan_selects_persistent_kernel_for_flagship_shape():
     assert engine.forward_plan(x, p, None, layout="IH", batch_first=True) in ("smem", "tcgen05")
     p2 = {k: v.to(dev()) for k, v in O.init_params(30, 96).tensors().items()}
     assert engine.forward_plan(torch.zeros(4, 5, 30, device=dev()), p2, None, layout="IH", batch_first=True) == "generic"
+
+
+@pytest.mark.parametrize("B,T,I,wR,uR,layout,bf,gate,xbf16", [
+    (150, 12, 32, 16, 32, "IH", True, "sigmoid", False),    # C4 ranks, three CTAs, ragged last one
+    (64, 3, 32, 16, 32, "HI", False, "sigmoid", False),     # FastGRNNCUDA layout, time-major
+    (70, 6, 16, 8, 16, "IH", True, "tanh", False),          # other ranks, tanh gate (generic activations)
+    (40, 9, 64, 32, 32, "HI", True, "sigmoid", True),       # I = 64, bf16 input
+])
+def test_lowrank_ffma_path_vs_oracle_and_generic(B, T, I, wR, uR, layout, bf, gate, xbf16):
+    """H = 256 low-rank forward on the persistent FFMA kernel (fgrnn_lr.cu): against the oracle's factored evaluation
+    (rnn.py:280-287) and against the generic kernel, with saved gates and the last state."""
+    from kws_b200 import _lib, engine
+    torch.manual_seed(77 + B + T)
+    p = O.init_params(I, 256, wR, uR)
+    p.bias_gate.add_(0.2 * torch.randn(1, 256)); p.bias_update.add_(0.2 * torch.randn(1, 256))
+    x = torch.randn(B, T, I) if bf else torch.randn(T, B, I)
+    if xbf16:
+        x = x.bfloat16().float()
+    h0 = 0.5 * torch.randn(B, 256)
+    ref = O.unroll(x, p, h0.clone().unsqueeze(0), bf, gate, "tanh")
+    tens = p.tensors() if layout == "IH" else O.to_cuda_layout(p)
+    params = {k: v.to(dev()).contiguous() for k, v in tens.items()}
+    xg = x.to(dev()).bfloat16() if xbf16 else x.to(dev())
+    h0g = h0.to(dev())
+    kw = dict(layout=layout, batch_first=bf, gate_nl=gate, update_nl="tanh")
+    assert engine.forward_plan(xg, params, h0g, **kw) == "lowrank"
+    out, z_s, c_s, last = engine.forward(xg, params, h0g, want_last=True, save_for_backward=True, **kw)
+    gen, z_g, c_g, _ = engine.forward(xg, params, h0g, save_for_backward=True, force_path=_lib.PATH_GENERIC, **kw)
+    torch.cuda.synchronize()
+    assert state_ratio(out, ref) <= 1.0, state_ratio(out, ref)
+    assert state_ratio(out, gen.cpu()) <= 1.0
+    assert state_ratio(z_s, z_g.cpu()) <= 1.0 and state_ratio(c_s, c_g.cpu()) <= 1.0
+    assert torch.equal(last, out[:, -1] if bf else out[-1])
+    # shapes the kernel does not cover keep the generic path
+    big = O.init_params(64, 256, 32, 64)
+    assert engine.forward_plan(torch.randn(4, 2, 64, device=dev()), {k: v.to(dev()) for k, v in big.tensors().items()},
+                               None, layout="IH", batch_first=True) == "generic"
