@@ -351,7 +351,7 @@ def test_auto_plan_selects_persistent_kernel_for_flagship_shape():
     (150, 12, 32, 16, 32, "IH", True, "sigmoid", False),    # C4 ranks, three CTAs, ragged last one
     (64, 3, 32, 16, 32, "HI", False, "sigmoid", False),     # FastGRNNCUDA layout, time-major
     (70, 6, 16, 8, 16, "IH", True, "tanh", False),          # other ranks, tanh gate (generic activations)
-    (40, 9, 64, 32, 32, "HI", True, "sigmoid", True),       # I = 64, bf16 input
+    (40, 9, 64, 16, 32, "HI", True, "sigmoid", True),       # I = 64 (the largest shape that fits shared memory), bf16 input
 ])
 def test_lowrank_ffma_path_vs_oracle_and_generic(B, T, I, wR, uR, layout, bf, gate, xbf16):
     """H = 256 low-rank forward on the persistent FFMA kernel (fgrnn_lr.cu): against the oracle's factored evaluation
