@@ -64,11 +64,12 @@ __device__ __forceinline__ void lr_tile_4x4(float (&acc)[4][4], const float* A, 
   }
 }
 
-template <bool FAST_NL>
+// RU_, RW_, I_ != 0: compile-time shape (the C4 shape 32/16/32 folds every shared-memory stride into immediates)
+template <bool FAST_NL, int RU_, int RW_, int I_>
 __global__ void __launch_bounds__(LR_THREADS, 1) lr_fwd_kernel(const FwdArgs a, const int bm) {
   extern __shared__ __align__(16) float sm[];
   const Dims d = a.d;
-  const int I = d.I, rW = d.rW, rU = d.rU, R = rU + rW;
+  const int I = I_ ? I_ : d.I, rW = RW_ ? RW_ : d.rW, rU = RU_ ? RU_ : d.rU, R = rU + rW;
   const LrSmem L = lr_smem_layout(I, rW, rU);
   float *U1s = sm + L.U1, *W1s = sm + L.W1, *V2s = sm + L.V2, *h_s = sm + L.h, *s_s = sm + L.s, *x_s = sm + L.x;
   const int SP = L.SP;
@@ -262,13 +263,16 @@ int launch_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
   const bool fast = a.d.gate_nl == FGRNN_NL_SIGMOID && a.d.update_nl == FGRNN_NL_TANH;
   const int bm = lr_rows_per_cta(a.d.B);
   const unsigned grid = (unsigned)((a.d.B + bm - 1) / bm);
-  if (fast) {
-    FGRNN_CUDA_TRY(cudaFuncSetAttribute(lr_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lr_fwd_kernel<true><<<grid, LR_THREADS, smem, stream>>>(a, bm);
-  } else {
-    FGRNN_CUDA_TRY(cudaFuncSetAttribute(lr_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lr_fwd_kernel<false><<<grid, LR_THREADS, smem, stream>>>(a, bm);
-  }
+  const bool c4 = a.d.rU == 32 && a.d.rW == 16 && a.d.I == 32;
+  auto go = [&](auto kern) -> int {
+    FGRNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, LR_THREADS, smem, stream>>>(a, bm);
+    return FGRNN_OK;
+  };
+  int rc;
+  if (fast) rc = c4 ? go(lr_fwd_kernel<true, 32, 16, 32>) : go(lr_fwd_kernel<true, 0, 0, 0>);
+  else rc = c4 ? go(lr_fwd_kernel<false, 32, 16, 32>) : go(lr_fwd_kernel<false, 0, 0, 0>);
+  if (rc) return rc;
   FGRNN_LAUNCH_CHECK("lr_fwd_kernel");
   return FGRNN_OK;
 }
