@@ -293,15 +293,20 @@ def main():
         x_tm = x.transpose(0, 1).contiguous()
         labels = torch.randint(0, 13, (B,), device=device)
 
-    def step():
-        if not train:
-            engine.forward(x, params, None, layout=args.layout, batch_first=True, out=out, force_path=force)
-            return
+    dbg = (lambda m: print("[bench rank %d] %s" % (rank, m), file=sys.stderr, flush=True)) if os.environ.get("FGRNN_BENCH_DEBUG") else (lambda m: None)
+
+    def step_compute():                           # forward, loss head, BPTT: gradients land in the flat bucket
         bucket.zero()
         hs = layer(x_tm)
         logp = torch.nn.functional.log_softmax(head(hs[-1]), dim=1)      # model.py:228-230
         loss = torch.nn.functional.nll_loss(logp, labels)
         loss.backward()
+
+    def step():
+        if not train:
+            engine.forward(x, params, None, layout=args.layout, batch_first=True, out=out, force_path=force)
+            return
+        step_compute()
         if world > 1:
             bucket.all_reduce_mean()
         opt.step()
@@ -309,10 +314,26 @@ def main():
     graphed = False
     run_step = step
     if train and not args.no_graph:
-        try:                                      # the whole step as one CUDA graph (kws_b200/graphs.py)
+        try:                                      # the step as CUDA graphs (kws_b200/graphs.py)
             from kws_b200 import graphs
-            cap = graphs.CapturedStep(step, warmup=args.warmup)
-            run_step, graphed = cap, True
+            if world == 1:
+                cap = graphs.CapturedStep(step, warmup=args.warmup)
+                run_step, graphed = cap, True
+            else:
+                # data parallel: the NCCL all-reduce stays an ordinary launch between two captured graphs (a collective
+                # captured next to eager collectives on the same communicator hung on this pool's NCCL 2.28 / torch 2.11)
+                for _ in range(args.warmup):
+                    step()
+                cap = graphs.CapturedStep(step_compute, warmup=1)
+                cap_opt = graphs.CapturedStep(opt.step, warmup=1)
+                n_lib = cap.launches + cap_opt.launches
+
+                def run_step():
+                    cap()
+                    bucket.all_reduce_mean()
+                    cap_opt()
+                cap.launches = n_lib
+                graphed = True
         except Exception as e:                    # noqa: BLE001 -- report and time the eager step instead
             print("bench.py: CUDA-graph capture failed (%s); timing the eager step" % (e,), file=sys.stderr)
             run_step = step
@@ -322,9 +343,12 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(device)
 
+    dbg("graphed=%s" % graphed)
     for _ in range(args.warmup):
         run_step()
+    dbg("warmup done")
     barrier()
+    dbg("barrier done")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -332,7 +356,9 @@ def main():
     for i in range(args.steps):
         run_step()
         evs[i + 1].record()
+    dbg("timed loop enqueued")
     barrier()
+    dbg("timed loop done")
     launches = cap.launches * args.steps if graphed else _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     total_ms = evs[0].elapsed_time(evs[-1])
