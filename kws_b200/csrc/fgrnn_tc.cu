@@ -361,7 +361,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
   float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16] max|U|, max|W|, max|b_g - b_u| per epilogue warp
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler then knows it is warp uniform and keeps everything derived from it
+  // (MMA set / role, descriptors, barrier addresses) in uniform registers instead of R2UR-ing it per instruction
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int row0 = blockIdx.x * TC_ROWS;
   const bool hi_layout = a.layout == FGRNN_LAYOUT_HI;
   // barrier map
@@ -729,15 +731,17 @@ static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
 
 // Tile configuration.  The per-step chain of a CTA does not depend on how many SMs are busy, and a tcgen05.mma costs
 // the same ~19 cycles for N = 16 and N = 32, so:
-//   batch fits one wave of 32-row CTAs  -> 2 x 16-row sub-tiles (shortest chain: ~2400 cycles per step);
-//   larger batches                      -> 4 x 16-row sub-tiles, two MMA warp sets (~3000 cycles per step for 64 rows,
-//                                          the tensor pipe ~75 % busy), 5-8 % faster than 2 x 32-row sub-tiles.
+//   batch fits one wave of 32-row CTAs  -> 2 x 16-row sub-tiles (shortest chain: ~2050 cycles per step);
+//   larger batches                      -> 2 x 32-row sub-tiles (~3000 cycles per step for 64 rows).
+// 4 x 16-row sub-tiles with two MMA warp sets (~3150 cycles) was the faster multi-wave configuration while the MMA
+// warps still paid ~5 R2UR per MMA; with uniform descriptors 2 x 32 leads by 1-4 %.
 // FGRNN_TC_NS=16|32 and FGRNN_TC_NT=2|4 override (tests, benchmarks); NT=4 implies NS=16.
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
-  int ns = 16, nt = a.d.B <= 148 * 32 ? 2 : 4;
+  int ns = a.d.B <= 148 * 32 ? 16 : 32, nt = 2;
   if (const char* e = getenv("FGRNN_TC_NT")) { if (atoi(e) == 4) nt = 4; else if (atoi(e) == 2) nt = 2; }
-  if (const char* e = getenv("FGRNN_TC_NS")) { if (atoi(e) == 32) { ns = 32; nt = 2; } }
+  if (const char* e = getenv("FGRNN_TC_NS")) { if (atoi(e) == 32) ns = 32; else if (atoi(e) == 16) ns = 16; }
+  if (nt == 4) ns = 16;
   if (nt == 4) return launch_tc_fwd_ns<16, 4>(a, stream);
   return ns == 16 ? launch_tc_fwd_ns<16, 2>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);
 }

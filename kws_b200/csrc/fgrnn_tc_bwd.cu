@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
   const CtSmem L = ct_smem_layout(a.KI);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);      // [0,1] full, [2,3] empty, [4] done
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp uniform
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   const bool want_u = a.partU != nullptr, want_w = a.partW != nullptr;
 
@@ -328,7 +328,7 @@ static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& m
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   __shared__ uint32_t tmem_base_s;
   const Dims d = a.d;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // shuffle: provably warp uniform
   const int row0 = blockIdx.x * BR_ROWS;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   const int B_HREADY = 0, B_DFULL = 2, B_SFULL = 4, B_SEMPTY = 4 + BR_NB;      // operand ready | accumulators ready | ring
