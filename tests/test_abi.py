@@ -180,6 +180,14 @@ def test_plan_selection_between_kernel_families(lib):
     assert plan(gate_nl=2) == _lib.PATH_SMEM                                 # tanh gate: not in the tensor-core epilogue
     assert plan(H=256, out_stride_b=768, out_stride_t=256) == _lib.PATH_GENERIC
     assert plan(rU=32, U1=0x1000, U2=0x1000) == _lib.PATH_GENERIC            # low rank
+    lr = dict(H=256, rW=16, rU=32, W1=0x1000, W2=0x1000, U1=0x1000, U2=0x1000, out_stride_b=768, out_stride_t=256)
+    assert plan(**lr) == _lib.PATH_LOWRANK                                   # C4 shape: persistent low-rank FFMA kernel
+    assert plan(**dict(lr, gate_nl=2)) == _lib.PATH_LOWRANK                  # every nonlinearity
+    assert plan(**dict(lr, rU=30)) == _lib.PATH_GENERIC                      # rank not a multiple of 4
+    assert plan(**dict(lr, I=64, rW=32, rU=64, x_stride_b=192, x_stride_t=64)) == _lib.PATH_GENERIC   # does not fit shared memory
+    assert plan(**dict(lr, U1=0x1004)) == _lib.PATH_GENERIC                  # weights not 16-byte aligned
+    assert plan(**dict(lr, force_path=_lib.PATH_GENERIC)) == _lib.PATH_GENERIC
+    assert plan(force_path=_lib.PATH_LOWRANK) == -1                          # full-rank problem forced onto the low-rank family
     assert plan(force_path=_lib.PATH_SMEM) == _lib.PATH_SMEM
     d = _fwd(I=28, x_stride_b=84, x_stride_t=28, force_path=_lib.PATH_TCGEN05)
     assert lib.fgrnn_forward(C.byref(d), None) == _lib.ERR_SHAPE and lib.fgrnn_forward_plan(C.byref(d)) == -1
@@ -195,3 +203,6 @@ def test_plan_selection_between_kernel_families(lib):
     g.grad_stride_b = 384
     g.p.gate_nl = 2
     assert lib.fgrnn_backward_plan(C.byref(g)) == _lib.PATH_SMEM
+    g.p.gate_nl = 0
+    g.p.force_path = _lib.PATH_LOWRANK                                       # forward-only family: backward plans generic
+    assert lib.fgrnn_backward_plan(C.byref(g)) == _lib.PATH_GENERIC
