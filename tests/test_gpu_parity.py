@@ -382,3 +382,24 @@ def test_lowrank_ffma_path_vs_oracle_and_generic(B, T, I, wR, uR, layout, bf, ga
     big = O.init_params(64, 256, 32, 64)
     assert engine.forward_plan(torch.randn(4, 2, 64, device=dev()), {k: v.to(dev()) for k, v in big.tensors().items()},
                                None, layout="IH", batch_first=True) == "generic"
+
+
+def test_lowrank_ffma_path_extreme_biases():
+    """The low-rank kernel's fused sigmoid/tanh (one EX2 + one RCP per element) is taken per thread only when its four
+    units have |b_g - b_u| <= 8; far-apart biases and saturated gates must still meet the tolerance."""
+    from kws_b200 import engine
+    torch.manual_seed(5)
+    p = O.init_params(32, 256, 16, 32)
+    p.bias_gate[0, :8] += 12.0           # distance > 8: these unit groups use the two-EX2 form
+    p.bias_update[0, 8:16] -= 15.0
+    p.bias_gate[0, 16:24] -= 30.0        # gate saturated at 0: e_g clamps at 2^30
+    p.bias_gate[0, 24:32] += 30.0        # gate saturated at 1
+    p.bias_update[0, 32:40] += 7.5       # inside the fused range, large ratio
+    x = 4.0 * torch.randn(37, 11, 32)
+    ref = O.unroll(x, p, None, True)
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    assert engine.forward_plan(x.to(dev()), params, None, layout="IH", batch_first=True) == "lowrank"
+    out = engine.forward(x.to(dev()), params, None, layout="IH", batch_first=True)[0]
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert state_ratio(out, ref) <= 1.0, state_ratio(out, ref)
