@@ -18,14 +18,17 @@ template <int BM>
 __device__ __forceinline__ void tile_mac(float (&acc)[BM], const float* __restrict__ A_s, int lda,
                                          const float* __restrict__ Wg, int ldw, int K, int n) {
   int k = 0;
-  for (; k + 4 <= K; k += 4) {
-    const float w0 = __ldg(Wg + (size_t)(k + 0) * ldw + n);
-    const float w1 = __ldg(Wg + (size_t)(k + 1) * ldw + n);
-    const float w2 = __ldg(Wg + (size_t)(k + 2) * ldw + n);
-    const float w3 = __ldg(Wg + (size_t)(k + 3) * ldw + n);
+  const float* __restrict__ wp = Wg + n;               // walks down column n: one 64-bit add per 4 k instead of four IMAD.WIDE
+  const size_t step4 = (size_t)4 * ldw;
+  const float* ap = A_s;
+  for (; k + 4 <= K; k += 4, wp += step4, ap += 4) {
+    const float w0 = __ldg(wp);
+    const float w1 = __ldg(wp + ldw);
+    const float w2 = __ldg(wp + 2 * ldw);
+    const float w3 = __ldg(wp + 3 * ldw);
 #pragma unroll
     for (int r = 0; r < BM; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(A_s + r * lda + k);
+      const float4 a = *reinterpret_cast<const float4*>(ap + r * lda);
       acc[r] = fmaf(a.x, w0, acc[r]);
       acc[r] = fmaf(a.y, w1, acc[r]);
       acc[r] = fmaf(a.z, w2, acc[r]);
