@@ -341,42 +341,59 @@ int launch_gemm_tn_partial(const TnArgs& a, int nchunk, cudaStream_t stream) {
   return FGRNN_OK;
 }
 
-constexpr int NT_TM = 64, NT_TI = 64, NT_NB = 16, NT_LD = 68;
+constexpr int NT_TM = 64, NT_NB = 16, NT_LD = 68;
 
+// dx[m][i] = sum_n dpre[m][n] * Wf[i][n]  (cu:552 d_input).  Tile = 64 rows x TI input features (TI = 32 when I <= 32:
+// the flagship I = 32 would waste half of a 64-wide tile), 16 n per pass; 16-byte global loads along n when N % 4 == 0.
+template <int TI>
 __global__ void __launch_bounds__(256) gemm_nt_kernel(const NtArgs a) {
+  constexpr int CJ = TI / 16;                         // output columns per thread
   __shared__ __align__(16) float Ds[NT_NB][NT_LD];   // [n][m]
   __shared__ __align__(16) float Ws[NT_NB][NT_LD];   // [n][i]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * NT_TM, i0 = blockIdx.y * NT_TI;
-  float acc[4][4];
+  const int m0 = blockIdx.x * NT_TM, i0 = blockIdx.y * TI;
+  const bool vec = (a.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.dpre) | reinterpret_cast<uintptr_t>(a.Wf)) & 15) == 0;
+  float acc[4][CJ];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < CJ; ++j) acc[i][j] = 0.0f;
   for (int nb = 0; nb < a.N; nb += NT_NB) {
-#pragma unroll
-    for (int q = 0; q < (NT_TM * NT_NB) / 256; ++q) {
-      const int e = tid + q * 256;
-      const int r = e / NT_NB, nn = e - r * NT_NB;
-      float dv = 0.0f, wv = 0.0f;
-      if (nb + nn < a.N) {
-        if (m0 + r < a.M) dv = a.dpre[(size_t)(m0 + r) * a.N + nb + nn];
-        if (i0 + r < a.I) wv = a.Wf[(size_t)(i0 + r) * a.N + nb + nn];
+    if (vec) {                                        // one float4 of dpre (and of W for the first TI rows) per thread
+      const int r = tid >> 2, n4 = (tid & 3) * 4;
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), wv = dv;
+      if (nb + n4 < a.N) {
+        if (m0 + r < a.M) dv = *reinterpret_cast<const float4*>(a.dpre + (size_t)(m0 + r) * a.N + nb + n4);
+        if (r < TI && i0 + r < a.I) wv = __ldg(reinterpret_cast<const float4*>(a.Wf + (size_t)(i0 + r) * a.N + nb + n4));
       }
-      Ds[nn][r] = dv;
-      Ws[nn][r] = wv;
+      Ds[n4 + 0][r] = dv.x; Ds[n4 + 1][r] = dv.y; Ds[n4 + 2][r] = dv.z; Ds[n4 + 3][r] = dv.w;
+      if (r < TI) { Ws[n4 + 0][r] = wv.x; Ws[n4 + 1][r] = wv.y; Ws[n4 + 2][r] = wv.z; Ws[n4 + 3][r] = wv.w; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < (NT_TM * NT_NB) / 256; ++q) {
+        const int e = tid + q * 256;
+        const int r = e / NT_NB, nn = e - r * NT_NB;
+        float dv = 0.0f, wv = 0.0f;
+        if (nb + nn < a.N) {
+          if (m0 + r < a.M) dv = a.dpre[(size_t)(m0 + r) * a.N + nb + nn];
+          if (r < TI && i0 + r < a.I) wv = a.Wf[(size_t)(i0 + r) * a.N + nb + nn];
+        }
+        Ds[nn][r] = dv;
+        if (r < TI) Ws[nn][r] = wv;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int nn = 0; nn < NT_NB; ++nn) {
       const float4 dv = *reinterpret_cast<const float4*>(&Ds[nn][ty * 4]);
-      const float4 wv = *reinterpret_cast<const float4*>(&Ws[nn][tx * 4]);
       const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-      const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      float ww[CJ];
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) ww[j] = Ws[nn][tx * CJ + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dd[i], ww[j], acc[i][j]);
+        for (int j = 0; j < CJ; ++j) acc[i][j] = fmaf(dd[i], ww[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -386,16 +403,21 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const NtArgs a) {
     if (m >= a.M) continue;
     const int t = m / a.B, b = m - t * a.B;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ii = i0 + tx * 4 + j;
+    for (int j = 0; j < CJ; ++j) {
+      const int ii = i0 + tx * CJ + j;
       if (ii < a.I) a.dx[(size_t)b * a.dsb + (size_t)t * a.dst + ii] = acc[i][j];
     }
   }
 }
 
 int launch_gemm_nt(const NtArgs& a, cudaStream_t stream) {
-  dim3 grid((a.M + NT_TM - 1) / NT_TM, (a.I + NT_TI - 1) / NT_TI);
-  gemm_nt_kernel<<<grid, 256, 0, stream>>>(a);
+  if (a.I <= 32) {
+    dim3 grid((a.M + NT_TM - 1) / NT_TM, 1);
+    gemm_nt_kernel<32><<<grid, 256, 0, stream>>>(a);
+  } else {
+    dim3 grid((a.M + NT_TM - 1) / NT_TM, (a.I + 63) / 64);
+    gemm_nt_kernel<64><<<grid, 256, 0, stream>>>(a);
+  }
   FGRNN_LAUNCH_CHECK("gemm_nt_kernel");
   return FGRNN_OK;
 }
