@@ -163,6 +163,11 @@ FGRNN_API int fgrnn_abi_version(void);
 /* Cumulative number of kernels this library has launched in this process. */
 FGRNN_API uint64_t fgrnn_launch_count(void);
 
+/* Diagnostic (tests only): fill every SM's tensor memory and shared memory with a NaN pattern, enqueued on
+   `stream`, so that the next launch cannot be saved by operands a predecessor left on chip.  The reference
+   has no counterpart; the first-launch parity tests call it between launches. */
+FGRNN_API int fgrnn_debug_poison_onchip(int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,8 @@ PATH_AUTO, PATH_GENERIC, PATH_SMEM, PATH_TCGEN05, PATH_LOWRANK = -1, 0, 1, 2, 3
 PATH_NAMES = {0: "generic", 1: "smem", 2: "tcgen05", 3: "lowrank"}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfastgrnn_b200.so")
+# KWS_B200_LIB points the binding at another build of the same library (developer builds: `make fuzz`)
+LIB_PATH = os.environ.get("KWS_B200_LIB") or os.path.join(_HERE, "lib", "libfastgrnn_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 _fp = C.c_void_p   # device pointers travel as integers
@@ -80,6 +81,7 @@ SYMBOLS = {
     "fgrnn_last_error_detail": (C.c_char_p, []),
     "fgrnn_abi_version": (C.c_int, []),
     "fgrnn_launch_count": (C.c_uint64, []),
+    "fgrnn_debug_poison_onchip": (C.c_int, [C.c_int, C.c_void_p]),
 }
 
 _lib = None

@@ -105,11 +105,15 @@ bool smem_fwd_ok(const FgrnnForward& f) {
          aligned16(f.h_last) && aligned16(f.save_z) && aligned16(f.save_c) && (!f.save_z == !f.save_c);
 }
 
+// the tcgen05 kernels keep output offsets in 32-bit registers: byte strides and B*H*4 must stay below 2^32
+bool fits_u32_bytes(int64_t elems) { return elems >= 0 && elems < ((int64_t)1 << 30); }
+
 // tcgen05 family: same streaming requirements; x is fetched by TMA (16-byte aligned base and strides)
 bool tc_fwd_ok(const FgrnnForward& f) {
   const FgrnnProblem& p = f.p;
   return smem_fwd_ok(f) && tc_path_supports(dims_of(p)) &&
-         tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T);
+         tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T) &&
+         fits_u32_bytes(f.out_stride_b) && fits_u32_bytes(f.out_stride_t) && fits_u32_bytes((int64_t)p.B * p.H);
 }
 
 // low-rank FFMA family: 16-byte vector access on x, h0 and every output; weights are copied from their canonical form
@@ -195,6 +199,13 @@ bool tc_contract_ok(const FgrnnBackward& g) {
 bool tc_bwd_ok(const FgrnnBackward& g) {
   const FgrnnProblem& p = g.p;
   if (!tc_bwd_rec_supports(dims_of(p))) return false;
+  // grad_h and the hidden states are fetched through TMA maps built from the caller's strides: the same
+  // requirements as the forward's x map (positive strides, 16-byte multiples) -- an expanded gradient with a
+  // zero stride (e.g. from out.sum((0,1)).backward()) falls through to the FFMA families instead of failing
+  // in cuTensorMapEncodeTiled after the path has been chosen
+  if (!tc_x_tma_ok(g.grad_h, g.grad_stride_b, g.grad_stride_t, FGRNN_F32, p.B, p.T)) return false;
+  if (g.hs && !tc_x_tma_ok(g.hs, g.hs_stride_b, g.hs_stride_t, FGRNN_F32, p.B, p.T)) return false;
+  if (!fits_u32_bytes((int64_t)p.B * p.H)) return false;
   return aligned16(p.U) && aligned16(p.h0) && aligned16(g.grad_h) && mult4(g.grad_stride_b) && mult4(g.grad_stride_t) &&
          aligned16(g.hs) && mult4(g.hs_stride_b) && mult4(g.hs_stride_t) && aligned16(g.z_s) && aligned16(g.c_s);
 }

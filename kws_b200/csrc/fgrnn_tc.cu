@@ -388,6 +388,20 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   // tcgen05 address warp-uniform (no R2UR in the MMA issue path).
   if (*tmem_base_s != 0u) __trap();
   constexpr uint32_t tmem = 0u;
+#ifdef FGRNN_TC_FUZZ
+  if (tid == 0) {
+    tc_progress()[30] = bar(0);
+    if (blockIdx.x == 0 && g_tc_stuck == 0) {
+      unsigned long long v0, v1, v2, v3;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v0) : "r"(bar(B_HREADY)) : "memory");
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v1) : "r"(bar(B_DFULL)) : "memory");
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v2) : "r"(bar(B_XFULL)) : "memory");
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v3) : "r"(bar(B_RAWFULL)) : "memory");
+      printf("tc_fwd<%d,%d> barriers at %u; fresh words: count %d -> %016llx, count %d -> %016llx, count %d -> %016llx, count 1 -> %016llx\n",
+             TC_NS, TC_NT, bar(0), TC_EPI_WARPS / TC_NT, v0, TC_MMA_ROLES, v1, TC_CONV_WARPS, v2, v3);
+    }
+  }
+#endif
 
   if (warp >= W_MMA) {
     // =========================== MMA issuers ======================================================
@@ -404,7 +418,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     const uint64_t dX0 = make_desc_kmajor(smem_u32(sm + L.x_op), KI);
     const uint32_t xlo_step = (uint32_t)L.x_tile_bytes >> 4, xtile_step = 2 * xlo_step, xbuf_step = TC_NT * xtile_step;
     const int variant = (nkx - 1) * 2 + (x_has_lo ? 1 : 0);
-    if (set) __nanosleep(set * TC_STAGGER2_NS);           // second set: a quarter period behind the first
+    if (set) tc_spin_ns(set * TC_STAGGER2_NS);           // second set: a quarter period behind the first
     for (int t = 0; t < d.T; ++t) {
       const int xb = t % TC_XBUF;
       mbar_wait(bar(B_XFULL + xb), (t / TC_XBUF) & 1); // x_t operand tiles written
@@ -418,7 +432,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
         TC_CRIT_WAIT(bar(B_HREADY + s), t & 1);        // h_{t-1} operand tile written, D of step t-1 drained
         tc_fence_after();
         if (role == 0 && set == 0) TC_TRACE(t, s, 9);
+        tc_mark(20);
         if (leader) {
+          tc_mark(21);
           if (TC_MMA_ROLES == 3) {
             if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
             else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
@@ -429,16 +445,21 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
             if (role == 0) issue_subtile_dispatch<3>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
             else issue_subtile_dispatch<4>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
           }
+          tc_mark(22);
           umma_commit1(bar(B_DFULL + s));              // implies tcgen05.fence::before_thread_sync
+          tc_mark(23);
         }
         __syncwarp();
+        tc_mark(24);
         if (role == 0 && set == 0) TC_TRACE(t, s, 10);
         // start the two sub-tile pipelines half a period apart so that one is in its MMA phase while the
         // other is in its epilogue (they keep the offset: nothing couples them but shared pipes)
-        if (t == 0 && ss == 0 && TC_SPS > 1) __nanosleep(TC_STAGGER_NS);
+        if (t == 0 && ss == 0 && TC_SPS > 1) tc_spin_ns(TC_STAGGER_NS);
       }
+      tc_mark(25);
       if (leader) umma_commit1(bar(B_XEMPTY + xb));    // this warp's MMAs have consumed the x_t tiles
       __syncwarp();
+      tc_mark(26);
     }
   } else if (warp >= W_CONV0) {
     // =========================== x path: TMA -> split -> operand tiles ============================

@@ -8,27 +8,114 @@
 
 namespace fgrnn {
 
+// Busy delay on the SM clock (~2 cycles per ns).  The tcgen05 kernels never execute a plain `nanosleep` in a warp
+// that issues tcgen05.mma / tcgen05.commit: measured in round 2 with the timing fuzzer (profiles/r02_first_launch_hunt.txt),
+// NANOSLEEP between an MMA burst and its commit plus NANOSLEEP before the next barrier check left all three issuing
+// warps blocked at their UTCHMMA / UTCBAR for good (a hard hang, never a wrong result), while the same delays spent
+// spinning on the clock are harmless.  mbarrier.try_wait's own suspend (NANOSLEEP.SYNCS) is not affected.
+__device__ __forceinline__ void tc_spin_ns(unsigned ns) {
+  if (ns == 0u) return;
+  const long long until = clock64() + 2ll * (long long)ns;
+  while (clock64() < until) { }
+}
+
+// ---- timing fuzzer (developer builds: make fuzz -> -DFGRNN_TC_FUZZ) -----------------------------------
+// Every synchronisation wrapper below calls tc_fuzz(site) first: a pseudo-random __nanosleep (1 in 16
+// calls up to 16 us, 3 in 16 up to 1 us) that shuffles the relative timing of the warp roles.  A protocol that is
+// correct gives bit-identical results under it (tools/first_launch_probe.cu compares against the quiet build).
+#ifdef FGRNN_TC_FUZZ
+static __device__ int g_tc_stuck = 0;      // set by the first wait that gives up; every later wait then returns at once
+// progress board: every warp leaves (calls so far, last site) where a stuck warp's report can read it
+__device__ __forceinline__ unsigned* tc_progress() { __shared__ unsigned board[2][32]; return &board[0][0]; }
+__device__ __forceinline__ void tc_mark(unsigned site) {
+  unsigned* b = tc_progress();
+  const unsigned w = threadIdx.x >> 5;
+  if (w < 32) { b[w] = b[w] + 1; b[32 + w] = site; }
+}
+#ifndef FGRNN_TC_FUZZ_SITES
+#define FGRNN_TC_FUZZ_SITES 0xffffffffu    // bit i: site i sleeps (1 arrive, 2 expect_tx, 3/4 wait entry/exit, 5/6 poll wait, 7 commit, 8 TMA)
+#endif
+__device__ __forceinline__ void tc_fuzz(unsigned site) {
+  tc_mark(site);
+  if (!((FGRNN_TC_FUZZ_SITES >> site) & 1u)) return;
+#ifdef FGRNN_TC_FUZZ_WARP_LO
+  if ((threadIdx.x >> 5) < FGRNN_TC_FUZZ_WARP_LO || (threadIdx.x >> 5) > FGRNN_TC_FUZZ_WARP_HI) return;
+#endif
+  unsigned c, sm;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  unsigned r = c ^ (sm * 0x9E3779B1u) ^ (site * 0x85EBCA6Bu) ^ ((threadIdx.x >> 5) * 0xC2B2AE35u);
+  r ^= r >> 15; r *= 0x2C1B3C6Du; r ^= r >> 12; r *= 0x297A2D39u; r ^= r >> 15;
+  // no shuffle: the lanes of a converged warp read the same %clock in the same issue slot, so r is warp uniform
+  // wherever the caller is (and where it is not, the lanes merely sleep for different times and reconverge)
+  const unsigned sel = r & 15u;
+  const unsigned ns = sel == 0u ? ((r >> 4) & 0x3fffu) : (sel < 4u ? ((r >> 4) & 0x3ffu) : 0u);
+#ifdef FGRNN_TC_FUZZ_NANOSLEEP          // see tc_spin_ns(): plain NANOSLEEP in the MMA-issuing warps can wedge tcgen05 issue
+  if (ns) __nanosleep(ns);
+#else
+  tc_spin_ns(ns);
+#endif
+}
+#else
+#define tc_fuzz(site) do { } while (0)
+#define tc_mark(site) do { } while (0)
+#endif
+#ifndef FGRNN_MBAR_SPIN_LIMIT
+#define FGRNN_MBAR_SPIN_LIMIT (1u << 20)     // x 20 us per try_wait: ~20 s before the protocol-bug guard traps
+#endif
+
 // ---- raw PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  tc_fuzz(1);
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  tc_fuzz(2);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Blocking wait: try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs
 // out, so waiting warps do not burn issue slots polling (an unhinted try_wait loop took 25 % of all issued
 // instructions away from the epilogue warps).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  tc_fuzz(3);
   uint32_t ok = 0;
+#ifdef FGRNN_TC_FUZZ
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
   for (uint32_t spins = 0; !ok; ++spins) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-    if (spins > (1u << 20)) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
+#ifdef FGRNN_TC_FUZZ
+    if (*(volatile int*)&g_tc_stuck) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (!ok && t1 - t0 > 2000000000ull) {     // fuzz build: 2 s of wall clock = deadlock; report who is stuck where and release everybody
+      if ((threadIdx.x & 31) == 0 && blockIdx.x < 4) {
+        printf("STUCK block %d warp %d barrier@%u parity %u after %u spins\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity, spins);
+        if (atomicAdd(&tc_progress()[31], 1u) == 0u) {     // first reporter of the CTA dumps the board and the barrier words
+          for (int w = 0; w < 24; ++w) printf("  board block %d warp %d: %u calls, last site %u\n", (int)blockIdx.x, w, tc_progress()[w], tc_progress()[32 + w]);
+          const uint32_t base = tc_progress()[30];
+          for (int i = 0; i < 32 && base; ++i) {
+            unsigned long long v;
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(base + 8 * i) : "memory");
+            printf("  mbarrier[%d] block %d = %016llx\n", i, (int)blockIdx.x, v);
+          }
+        }
+      }
+      __nanosleep(1000000);                  // let the other stuck warps report before everything is released
+      *(volatile int*)&g_tc_stuck = 1;
+      break;
+    }
+#else
+    if (spins > FGRNN_MBAR_SPIN_LIMIT) __trap();      // protocol bug guard: fail loudly instead of hanging the GPU
+#endif
   }
+  tc_fuzz(4);
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -38,12 +125,14 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 // Polling wait (no suspend hint) for barriers completed by bulk-copy transaction counts on the critical path
 __device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  tc_fuzz(5);
   uint32_t ok = 0;
   for (uint32_t spins = 0; !ok; ++spins) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (spins > (1u << 26)) __trap();
   }
+  tc_fuzz(6);
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -77,6 +166,7 @@ __device__ __forceinline__ void umma_ts1(uint32_t d_tmem, uint32_t a_tmem, uint6
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit1(uint32_t bar) {
+  tc_fuzz(7);
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // arrives on the mbarrier when every MMA issued so far by the elected lane has completed
@@ -108,15 +198,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  tc_fuzz(8);
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-// v*scale = hi + lo with hi, lo fp16 (round to nearest); two values at once
+// v*scale = hi + lo with hi, lo fp16 (round to nearest); two values at once.  No clamp: NaN stays NaN and a value
+// beyond the fp16 range (|v*scale| > 65504; weights are pre-scaled below 30000, so this means an input or state of
+// that size) becomes Inf - Inf = NaN in the lo part -- the result is NaN, as loud as the reference's own NaN/Inf
+// propagation, instead of a silently saturated finite number.
 __device__ __forceinline__ void split2(float a, float b, float scale, uint32_t& hi, uint32_t& lo) {
   a *= scale; b *= scale;
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);

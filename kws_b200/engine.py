@@ -212,8 +212,8 @@ def backward(grad_h: torch.Tensor, x: torch.Tensor, hs: torch.Tensor, z_s: torch
         raise RuntimeError("grad_h must be a CUDA tensor")
     if grad_h.dtype != torch.float32:
         grad_h = grad_h.float()
-    if grad_h.stride(2) != 1 and H > 1:
-        grad_h = grad_h.contiguous()
+    if (grad_h.stride(2) != 1 and H > 1) or 0 in grad_h.stride()[:2]:
+        grad_h = grad_h.contiguous()         # also materialises expanded gradients (stride 0 from sum/mean)
     if hs.stride(2) != 1 and H > 1:
         hs = hs.contiguous()
     exp = (B, T, H) if pr.batch_first else (T, B, H)

@@ -94,7 +94,7 @@ class GradBucket:
             return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
-            return work
+            return _MeanWork(work, self.flat, world)
         self.flat.div_(world)
         return None
 
@@ -104,6 +104,25 @@ class GradBucket:
         self.flat.mul_(float(local_rows) / float(total_rows))
         if dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+class _MeanWork:
+    """Handle returned by ``GradBucket.all_reduce_mean(async_op=True)``: ``wait()`` completes the
+    sum AND applies the division by the world size, so a caller that waits and steps the optimizer
+    sees the same mean gradient as the blocking call."""
+
+    def __init__(self, work, flat: torch.Tensor, world: int):
+        self._work, self._flat, self._world, self._done = work, flat, world, False
+
+    def wait(self) -> bool:
+        if not self._done:
+            self._work.wait()
+            self._flat.div_(self._world)
+            self._done = True
+        return True
+
+    def is_completed(self) -> bool:
+        return self._done or self._work.is_completed()
 
 
 def broadcast_parameters(params: Sequence[torch.Tensor], src: int = 0, group=None) -> None:
