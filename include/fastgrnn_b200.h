@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FGRNN_ABI_VERSION 1
+#define FGRNN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FGRNN_API __attribute__((visibility("default")))
@@ -80,7 +80,7 @@ enum { FGRNN_F32 = 0, FGRNN_BF16 = 1 };
 enum {
   FGRNN_PATH_GENERIC = 0,    /* any shape: weights streamed through L1/L2 */
   FGRNN_PATH_SMEM = 1,       /* persistent FFMA kernel, weights resident in shared memory */
-  FGRNN_PATH_TCGEN05 = 2,    /* tcgen05/TMEM kernel */
+  FGRNN_PATH_TCGEN05 = 2,    /* tcgen05/TMEM kernels: fused (H = 128, I <= 64) or hoisted x.W GEMM + recurrence (H = 128 / 256, I <= 256) */
   FGRNN_PATH_LOWRANK = 3     /* forward only: persistent FFMA kernel for W1.W2 / U1.U2 with H = 256 (backward: generic) */
 };
 
@@ -107,6 +107,13 @@ typedef struct FgrnnProblem {
   /* input sequence */
   const void* x;  int64_t x_stride_b, x_stride_t;          /* [B,T,I] by strides */
   const float* h0;           /* [B,H] contiguous, NULL = zeros (rnn.py:588-591, rnn.py:816-818) */
+  /* optional per-unit factors on the two pre-activations, [1,H] each, NULL = 1:
+       z = gate(gate_scale * pre + bias_gate),  c = update(update_scale * pre + bias_update).
+     This is what the reference's FastGRNNBatchNormCell computes in eval mode (rnn.py:377-408) once its four
+     BatchNorm1d layers are folded: bn_w / bn_u scale the columns of W / U, bn_gate / bn_update become these
+     factors plus shifts of the two biases (kws_b200/rnn.py FastGRNNBatchNorm does the folding).  Forward only. */
+  const float* gate_scale;
+  const float* update_scale;
 } FgrnnProblem;
 
 /* forward (replaces forward / forward_unroll, cuda/fastgrnn_cuda.cpp:73,147) */

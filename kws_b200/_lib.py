@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (include/fastgrnn_b200.h)
 OK, ERR_NULL, ERR_SHAPE, ERR_ENUM, ERR_ALIGN, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE, ERR_VERSION = range(9)
@@ -42,6 +42,7 @@ class FgrnnProblem(C.Structure):
         ("bias_gate", _fp), ("bias_update", _fp), ("zeta", _fp), ("nu", _fp),
         ("x", _fp), ("x_stride_b", C.c_int64), ("x_stride_t", C.c_int64),
         ("h0", _fp),
+        ("gate_scale", _fp), ("update_scale", _fp),
     ]
 
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "fgrnn_kernels.cuh"
@@ -87,6 +88,8 @@ struct DeviceGuard {
 // ----------------------------------------------------------------------------------------
 struct FwdPlan {
   int path;
+  bool tc_wide;               // tcgen05 family, hoisted-projection kernels (fgrnn_tc_wx.cu)
+  float* wx;                  // [T][B][H] workspace of the hoisted input projection
   // canonical weight pointers (either the caller's or workspace copies)
   float *Wc, *Uc, *W1c, *W2c, *U1c, *U2c;
   size_t ws_bytes;
@@ -96,9 +99,11 @@ bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15)
 bool mult4(int64_t v) { return (v & 3) == 0; }
 
 // the persistent shared-memory family needs 16-byte vector access on every streamed tensor
+bool has_scales(const FgrnnProblem& p) { return p.gate_scale || p.update_scale; }
+
 bool smem_fwd_ok(const FgrnnForward& f) {
   const FgrnnProblem& p = f.p;
-  if (!smem_path_supports(dims_of(p))) return false;
+  if (has_scales(p) || !smem_path_supports(dims_of(p))) return false;
   const bool xok = p.x_dtype == FGRNN_BF16 ? (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 : aligned16(p.x);
   return xok && mult4(p.x_stride_b) && mult4(p.x_stride_t) && aligned16(p.W) && aligned16(p.U) &&
          aligned16(p.h0) && aligned16(f.out) && mult4(f.out_stride_b) && mult4(f.out_stride_t) &&
@@ -116,10 +121,18 @@ bool tc_fwd_ok(const FgrnnForward& f) {
          fits_u32_bytes(f.out_stride_b) && fits_u32_bytes(f.out_stride_t) && fits_u32_bytes((int64_t)p.B * p.H);
 }
 
+// tcgen05 family, wide shapes: x by TMA; everything else is accessed element-wise (4-byte alignment)
+bool tc_wide_ok(const FgrnnForward& f) {
+  const FgrnnProblem& p = f.p;
+  return tc_wide_supports(dims_of(p)) && tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T) &&
+         fits_u32_bytes(f.out_stride_b) && fits_u32_bytes(f.out_stride_t) && fits_u32_bytes((int64_t)p.B * p.H) &&
+         (!f.save_z == !f.save_c);
+}
+
 // low-rank FFMA family: 16-byte vector access on x, h0 and every output; weights are copied from their canonical form
 bool lr_fwd_ok(const FgrnnForward& f) {
   const FgrnnProblem& p = f.p;
-  if (!lr_path_supports(dims_of(p))) return false;
+  if (has_scales(p) || !lr_path_supports(dims_of(p))) return false;
   const bool xok = p.x_dtype == FGRNN_BF16 ? (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 : aligned16(p.x);
   return xok && mult4(p.x_stride_b) && mult4(p.x_stride_t) && aligned16(p.W1) && aligned16(p.W2) && aligned16(p.U1) &&
          aligned16(p.U2) && aligned16(p.bias_gate) && aligned16(p.bias_update) && aligned16(p.h0) && aligned16(f.out) &&
@@ -129,7 +142,7 @@ bool lr_fwd_ok(const FgrnnForward& f) {
 
 int select_fwd_path(const FgrnnForward& f) {
   if (f.p.force_path >= 0) return f.p.force_path;
-  if (tc_fwd_ok(f)) return FGRNN_PATH_TCGEN05;
+  if (tc_fwd_ok(f) || tc_wide_ok(f)) return FGRNN_PATH_TCGEN05;
   if (lr_fwd_ok(f)) return FGRNN_PATH_LOWRANK;       // 5x the FFMA family at C2, faster per step even for one CTA
   return smem_fwd_ok(f) ? FGRNN_PATH_SMEM : FGRNN_PATH_GENERIC;
 }
@@ -139,6 +152,10 @@ FwdPlan plan_forward(const FgrnnForward& f, void* ws) {
   FwdPlan pl{};
   pl.path = select_fwd_path(f);
   Carver cv(ws);
+  pl.tc_wide = pl.path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f);
+  if (pl.path == FGRNN_PATH_TCGEN05 && !pl.tc_wide && tc_wide_ok(f))
+    if (const char* e = getenv("FGRNN_TC_WIDE")) pl.tc_wide = atoi(e) != 0;      // tests: hoisted kernels on a shape the fused kernel covers
+  if (pl.tc_wide) pl.wx = cv.take<float>(tc_wide_workspace_floats(dims_of(p)));
   if (p.weight_layout == FGRNN_LAYOUT_HI && (pl.path == FGRNN_PATH_GENERIC || pl.path == FGRNN_PATH_LOWRANK)) {
     if (p.rW == 0) pl.Wc = cv.take<float>((size_t)p.I * p.H);
     else { pl.W1c = cv.take<float>((size_t)p.I * p.rW); pl.W2c = cv.take<float>((size_t)p.rW * p.H); }
@@ -158,8 +175,10 @@ int validate_forward(const FgrnnForward& f) {
     return fail(FGRNN_ERR_SHAPE, "forced shared-memory path needs full-rank H=128, I%%4==0, I<=64 and 16-byte aligned tensors");
   if (path == FGRNN_PATH_LOWRANK && !lr_fwd_ok(f))
     return fail(FGRNN_ERR_SHAPE, "forced low-rank path needs H=256, wRank%%4==0 (<=32), uRank%%4==0 (<=64), I%%4==0 (<=64) and 16-byte aligned tensors");
-  if (path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f))
-    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full-rank H=128, I%%8==0, I<=64, sigmoid gate / tanh update, 16-byte aligned tensors and strides");
+  if (path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f) && !tc_wide_ok(f))
+    return fail(FGRNN_ERR_SHAPE, "forced tcgen05 path needs full rank, H=128 or 256, I%%8==0, I<=256, sigmoid or tanh gate, tanh update, 16-byte aligned input rows");
+  if (has_scales(f.p) && path != FGRNN_PATH_GENERIC && !(path == FGRNN_PATH_TCGEN05 && tc_wide_ok(f)))
+    return fail(FGRNN_ERR_SHAPE, "gate_scale / update_scale are supported by the generic and the wide tcgen05 kernels only");
   return FGRNN_OK;
 }
 
@@ -253,6 +272,7 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
 int validate_backward(const FgrnnBackward& g) {
   int rc = validate_problem(g.p);
   if (rc) return rc;
+  if (has_scales(g.p)) return fail(FGRNN_ERR_SHAPE, "gate_scale / update_scale (folded eval-mode BatchNorm) are forward only");
   if ((int64_t)g.p.B * g.p.T > 0) {
     if (!g.grad_h) return fail(FGRNN_ERR_NULL, "grad_h must be a CUDA tensor (NULL)");
     if (!g.hs && g.p.T > 1) return fail(FGRNN_ERR_NULL, "hidden_states must be a CUDA tensor (NULL)");
@@ -370,12 +390,14 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     s.x = p.x; s.xsb = p.x_stride_b; s.xst = p.x_stride_t; s.h0 = p.h0;
     s.out = f->out; s.osb = f->out_stride_b; s.ost = f->out_stride_t;
     s.h_last = f->h_last; s.save_z = f->save_z; s.save_c = f->save_c;
+    if (pl.tc_wide) return launch_tc_wide_fwd(s, p.gate_scale, p.update_scale, pl.wx, stream);
     return pl.path == FGRNN_PATH_TCGEN05 ? launch_tc_fwd(s, stream) : launch_smem_fwd(s, stream);
   }
 
   FwdArgs a{};
   a.d = dims_of(p);
   a.bias_gate = p.bias_gate; a.bias_update = p.bias_update; a.zeta = p.zeta; a.nu = p.nu;
+  a.gate_scale = p.gate_scale; a.update_scale = p.update_scale;
   a.x = p.x; a.xsb = p.x_stride_b; a.xst = p.x_stride_t;
   a.h0 = p.h0;
   a.out = f->out; a.osb = f->out_stride_b; a.ost = f->out_stride_t;

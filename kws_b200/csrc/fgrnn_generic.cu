@@ -117,12 +117,13 @@ __global__ void __launch_bounds__(GEN_NT) gen_fwd_kernel(const FwdArgs a) {
       if (d.rU == 0) tile_mac<BM>(accu, hc, Hp, a.Uc, d.H, d.H, n);          // rnn.py:284
       else           tile_mac<BM>(accu, tu_s, rUp, a.U2c, d.H, d.rU, n);     // rnn.py:286-287
       const float bg = __ldg(a.bias_gate + n), bu = __ldg(a.bias_update + n);
+      const float sg = a.gate_scale ? __ldg(a.gate_scale + n) : 1.0f, su = a.update_scale ? __ldg(a.update_scale + n) : 1.0f;
 #pragma unroll
       for (int r = 0; r < BM; ++r) {
         if (r < nrows) {
           const float pre = accw[r] + accu[r];                               // rnn.py:289
-          const float z = act_rt(d.gate_nl, pre + bg);                       // rnn.py:290
-          const float c = act_rt(d.update_nl, pre + bu);                     // rnn.py:292
+          const float z = act_rt(d.gate_nl, fmaf(sg, pre, bg));              // rnn.py:290 (sg, su: folded BatchNorm, rnn.py:402-408)
+          const float c = act_rt(d.update_nl, fmaf(su, pre, bu));            // rnn.py:292
           const float hold = hc[r * Hp + n];
           const float hnew = z * hold + (sz * (1.0f - z) + sn) * c;          // rnn.py:294-295
           hn[r * Hp + n] = hnew;

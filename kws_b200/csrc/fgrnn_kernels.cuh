@@ -10,6 +10,7 @@ struct FwdArgs {
   // canonical weights, row-major [K][N]:  Wc[I][H] | W1c[I][rW], W2c[rW][H];  Uc[H][H] | U1c[H][rU], U2c[rU][H]
   const float *Wc, *Uc, *W1c, *W2c, *U1c, *U2c;
   const float *bias_gate, *bias_update, *zeta, *nu;
+  const float *gate_scale, *update_scale;     // optional per-unit factors on the pre-activations (null = 1)
   const void* x; int64_t xsb, xst;
   const float* h0;
   float* out; int64_t osb, ost;
@@ -118,6 +119,10 @@ int launch_smem_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 bool tc_path_supports(const Dims& d);
 bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, int T);
 int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream);
+// wide shapes (fgrnn_tc_wx.cu): hoisted x.W GEMM + WX-stream recurrence; H = 128 or 256 (CTA pair), I <= 256
+bool tc_wide_supports(const Dims& d);
+size_t tc_wide_workspace_floats(const Dims& d);
+int launch_tc_wide_fwd(const SmemFwdArgs& a, const float* gate_scale, const float* update_scale, float* wx_ws, cudaStream_t stream);
 
 // T-parallel contractions dW, dU on the tensor cores (fgrnn_tc_bwd.cu); partials in the canonical orientation,
 // one per CTA, summed by launch_reduce

@@ -275,14 +275,14 @@ static inline EncodeTiledFn encode_tiled_fn() {
 // step.  The two outer dimensions are ordered by stride; *time_outer tells the kernel the coordinate order:
 // 0 -> {0, t, row}, 1 -> {0, row, t}.  Rows past the end are zero-filled by the TMA unit.
 static inline int make_row_tile_map(CUtensorMap* map, const void* base, bool bf16, int inner, int rows, int steps,
-                                    int64_t row_stride, int64_t step_stride, int box_rows, int* time_outer) {
+                                    int64_t row_stride, int64_t step_stride, int box_rows, int* time_outer, int box_inner = 0) {
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) { set_error_detail("cuTensorMapEncodeTiled is not available from the driver"); return FGRNN_ERR_CUDA; }
   const int esz = bf16 ? 2 : 4;
   *time_outer = step_stride >= row_stride ? 1 : 0;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t box[3], estr[3] = {1, 1, 1};
-  gdim[0] = (cuuint64_t)inner; box[0] = (cuuint32_t)inner;
+  gdim[0] = (cuuint64_t)inner; box[0] = (cuuint32_t)(box_inner > 0 ? box_inner : inner);   // box_inner: a feature slab; past `inner` the TMA unit zero-fills
   if (*time_outer) {
     gdim[1] = (cuuint64_t)rows; gdim[2] = (cuuint64_t)steps;
     gstr[0] = (cuuint64_t)row_stride * esz; gstr[1] = (cuuint64_t)step_stride * esz;

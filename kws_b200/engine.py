@@ -96,6 +96,10 @@ class _Problem:
         self.t["bias_update"] = _check_param("bias_update", params["bias_update"], self.device, (1, H))
         self.t["zeta"] = _check_param("zeta", params["zeta"], self.device, (1, 1))
         self.t["nu"] = _check_param("nu", params["nu"], self.device, (1, 1))
+        # optional per-unit factors on the pre-activations (folded eval-mode BatchNorm, rnn.py:402-408)
+        for k in ("gate_scale", "update_scale"):
+            if _present(params.get(k)):
+                self.t[k] = _check_param(k, params[k], self.device, (1, H))
         if h0 is not None:
             h0 = _check_param("old_h", h0, self.device, (self.B, H))
         self.h0 = h0
@@ -122,6 +126,8 @@ class _Problem:
         p.x = self.x.data_ptr() if self.x.numel() else None
         p.x_stride_b, p.x_stride_t = self.strides(self.x)
         p.h0 = _ptr(self.h0)
+        p.gate_scale = _ptr(self.t.get("gate_scale"))
+        p.update_scale = _ptr(self.t.get("update_scale"))
 
 
 def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:

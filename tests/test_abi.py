@@ -177,8 +177,15 @@ def test_plan_selection_between_kernel_families(lib):
     assert plan(x_dtype=_lib.BF16, x=0x1000) == _lib.PATH_TCGEN05
     assert plan(I=28, x_stride_b=84, x_stride_t=28) == _lib.PATH_SMEM        # I % 8 != 0: FFMA family
     assert plan(x=0x1004) == _lib.PATH_GENERIC                               # x not 16-byte aligned: no vector / TMA access
-    assert plan(gate_nl=2) == _lib.PATH_SMEM                                 # tanh gate: not in the tensor-core epilogue
-    assert plan(H=256, out_stride_b=768, out_stride_t=256) == _lib.PATH_GENERIC
+    assert plan(gate_nl=2) == _lib.PATH_TCGEN05                              # tanh gate: hoisted-projection kernels (fgrnn_tc_wx.cu)
+    assert plan(H=256, out_stride_b=768, out_stride_t=256) == _lib.PATH_TCGEN05   # H = 256 full rank: CTA pair
+    assert plan(I=256, x_stride_b=768, x_stride_t=256) == _lib.PATH_TCGEN05  # the default model's second layer
+    assert plan(I=264, x_stride_b=792, x_stride_t=264) == _lib.PATH_GENERIC  # I > 256
+    assert plan(H=64, out_stride_b=192, out_stride_t=64) == _lib.PATH_GENERIC
+    assert plan(gate_nl=1) == _lib.PATH_SMEM                                 # relu gate: FFMA family
+    assert plan(gate_scale=0x1000) == _lib.PATH_TCGEN05                      # folded BatchNorm factors: wide tcgen05 or generic only
+    assert plan(gate_scale=0x1000, I=28, x_stride_b=84, x_stride_t=28) == _lib.PATH_GENERIC
+    assert plan(gate_scale=0x1000, force_path=_lib.PATH_SMEM) == -1
     assert plan(rU=32, U1=0x1000, U2=0x1000) == _lib.PATH_GENERIC            # low rank
     lr = dict(H=256, rW=16, rU=32, W1=0x1000, W2=0x1000, U1=0x1000, U2=0x1000, out_stride_b=768, out_stride_t=256)
     assert plan(**lr) == _lib.PATH_LOWRANK                                   # C4 shape: persistent low-rank FFMA kernel
