@@ -37,28 +37,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank)); return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  tc_fuzz(1);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_release_cluster_local(uint32_t bar) {
-  tc_fuzz(1);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// wait with cluster-scope acquire: the phase may be completed by the partner CTA's arrivals
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  tc_fuzz(3);
-  uint32_t ok = 0;
-  for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-    if (spins > FGRNN_MBAR_SPIN_LIMIT) __trap();
-  }
-  tc_fuzz(4);
+// Asynchronous 16-byte store into the partner CTA's shared memory; its completion is counted in bytes on the partner's
+// mbarrier (complete_tx), so the hand-off needs no cluster-scope release: a `mbarrier.arrive.release.cluster` (and a full
+// fence.proxy.async) compiles to MEMBAR.ALL.GPU, which waits for every global store of h_t / z_t / c_t still in flight --
+// measured 1.6 us per step on the critical chain of the first version of the pair kernel.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar) : "memory");
 }
 
 // =====================================================================================================================
@@ -208,15 +193,22 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
       mbar_wait(bar(B_XEMPTY + xb), ((u / XW_XBUF) & 1) ^ 1);
       const unsigned char* raw = raw_base + st * L.raw_stage_bytes;
       unsigned char* xdst = sm + L.x_op + xb * xbuf_bytes;
+      // 16 rows x 8 chunks of 8 features = 128 tasks, 4 per lane, on a DIAGONAL: the 8 lanes of a quarter warp take 8
+      // different rows AND 8 different chunks, so that both the 32-byte reads of the raw tile (row stride 256 B; the two
+      // 16-byte halves are read in opposite order by lanes 0-3 / 4-7) and the 16-byte writes into the K-major operand tile
+      // (8 consecutive rows of one chunk = 128 B) are free of bank conflicts (the row-major mapping cost 8 wavefronts per
+      // STS.128: 56 M excess wavefronts on the default model's second layer, 40 % of the kernel).
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int e = it * 32 + lane, row = e >> 3, ch = e & 7;
+        const int jj = lane & 7, row = (it & 1) * 8 + jj, ch = (jj + (lane >> 3) + 4 * (it >> 1)) & 7;
         if (ch < nch_slab) {
           float v[8];
           if (ch < nch_here && ch * 8 < boxi) {           // inside the TMA box (features past I are zero-filled by the TMA unit)
             const unsigned char* src = raw + (size_t)row * boxi * esz + ch * 8 * esz;
             if (esz == 4) {
-              const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 16);
+              const int sw = (jj >> 2) & 1;
+              const float4 pa = *reinterpret_cast<const float4*>(src + sw * 16), pb = *reinterpret_cast<const float4*>(src + (sw ^ 1) * 16);
+              const float4 p0 = sw ? pb : pa, p1 = sw ? pa : pb;
               v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
             } else {
               const uint4 p = *reinterpret_cast<const uint4*>(src);
@@ -284,9 +276,11 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
 
     const uint32_t acc0 = tmem + lane_base + XW_TM_ACC + es * 4 * XW_NS + rh * 16;
     int u = 0;
+    int t = (int)blockIdx.x / a.nrb, rb = (int)blockIdx.x - t * a.nrb;       // tile = t * nrb + rb, advanced without divisions
+    const int sub_row = es * XW_NS + rh * 16;
+    const size_t Hs = (size_t)H;
     for (int j = 0; j < my_tiles; ++j) {
-      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-      const int t = tile / a.nrb, row_first = (tile - t * a.nrb) * XW_ROWS + es * XW_NS + rh * 16;
+      const int row_first = rb * XW_ROWS + sub_row;
       float r[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) r[q] = 0.f;
@@ -308,10 +302,17 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_DEMPTY + es * 2 + db));
       }
-      float* dst = a.wx + ((size_t)t * d.B + row_first) * H + unit0 + n;
+      float* dst = a.wx + ((size_t)t * d.B + row_first) * Hs + unit0 + n;
+      if (row_first + 16 <= d.B) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (row_first + q < d.B) dst[(size_t)q * H] = r[q] * unscale;
+        for (int q = 0; q < 16; ++q) dst[q * Hs] = r[q] * unscale;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (row_first + q < d.B) dst[q * Hs] = r[q] * unscale;
+      }
+      rb += (int)gridDim.x;
+      while (rb >= a.nrb) { rb -= a.nrb; ++t; }
     }
   }
   tc_fence_before();
@@ -333,6 +334,8 @@ struct WxFwdArgs {
   float* h_last; float* save_z; float* save_c;
 };
 
+template <int V> struct IntTag { static constexpr int value = V; };
+template <bool V> struct BoolTag { static constexpr bool value = V; };
 constexpr int WXF_MMA_WARPS = 3;
 constexpr int WXF_THREADS = 32 * (WX_EPI_WARPS + 1 + WXF_MMA_WARPS);       // 640
 struct WxfSmem { int h_op, ring, bars, misc, total; int h_tile_bytes, ring_stage_bytes, stages, nbuf; };
@@ -367,7 +370,7 @@ struct TcWxFwd {
     return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
   }
 
-  struct EpiK { float2 un, kg, cg, ku, cu, msz, szn; float sg, bg, su, bu; };
+  struct EpiK { float2 un, kg, cg, ku, cu, msz, szn; float sg, bg, su, bu, tmin; };
 
   static __device__ __forceinline__ void run(const WxFwdArgs& a, const CUtensorMap& wxmap) {
     extern __shared__ __align__(128) unsigned char sm[];
@@ -381,14 +384,20 @@ struct TcWxFwd {
     const int row0 = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * ROWS;
     const int unit0 = (int)rank * WX_HC;
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    const int B_HREADY = 0, B_DFULL = 2, B_WXFULL = 4, B_WXEMPTY = 12;        // WX*: [sub-tile][stage]
+    // HREADY: [sub-tile][step parity] -- the pair kernel uses one barrier per operand buffer (a step's 16 KB from the
+    // partner are counted on the barrier of the buffer they land in, so traffic of adjacent steps can never mix);
+    // the single-CTA kernel uses [sub-tile][0] only.  WX*: [sub-tile][stage]
+    const int B_HREADY = 0, B_DFULL = 4, B_WXFULL = 6, B_WXEMPTY = 14;
+    auto hr_bar = [&](int s_, int t_) { return bar(B_HREADY + s_ * 2 + (PAIR ? (t_ & 1) : 0)); };
+    auto hr_parity = [&](int t_) { return (uint32_t)(PAIR ? (t_ >> 1) & 1 : t_ & 1); };
     constexpr int W_PROD = WX_EPI_WARPS, W_MMA = WX_EPI_WARPS + 1;
     constexpr int EPI_PER_TILE = WX_EPI_WARPS / WX_NT;
 
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), TMEM_COLS);
     if (tid == 0) {
       for (int s = 0; s < WX_NT; ++s) {
-        mbar_init(bar(B_HREADY + s), EPI_PER_TILE * (PAIR ? 2 : 1));
+        mbar_init(bar(B_HREADY + s * 2), EPI_PER_TILE);
+        mbar_init(bar(B_HREADY + s * 2 + 1), EPI_PER_TILE);
         mbar_init(bar(B_DFULL + s), WXF_MMA_WARPS);
         for (int st = 0; st < L.stages; ++st) { mbar_init(bar(B_WXFULL + s * 4 + st), 1); mbar_init(bar(B_WXEMPTY + s * 4 + st), EPI_PER_TILE); }
       }
@@ -414,7 +423,8 @@ struct TcWxFwd {
         for (int s = 0; s < WX_NT; ++s) {
           const uint64_t dHhi = dH0 + (uint64_t)((PAIR ? (t & 1) : 0) * hbuf_step + s * htile_step), dHlo = dHhi + hlo_step;
           const uint32_t acc = tmem + TM_ACC + s * TM_ACC_PER_TILE;
-          if (PAIR) mbar_wait_cluster(bar(B_HREADY + s), t & 1); else mbar_wait(bar(B_HREADY + s), t & 1);
+          mbar_wait(hr_bar(s, t), hr_parity(t));        // own half written by this CTA's epilogue, partner's half landed (tx bytes)
+          if (PAIR) fence_proxy_async_smem();           // the partner's st.async data (generic proxy) -> visible to tcgen05.mma
           tc_fence_after();
           if (leader) {
             if (role == 0) {
@@ -469,14 +479,20 @@ struct TcWxFwd {
       for (int k = part; k < HK; k += 4) mu = fmaxf(mu, fabsf(hi_layout ? __ldg(a.U + (size_t)gu * HK + k) : __ldg(a.U + (size_t)k * HK + gu)));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
-      if (lane == 0) red_s[ew] = mu;
+      // largest gate/update bias distance of any unit of this CTA: selects the activation form (fgrnn_tc.cu)
+      float bd = part == 0 ? fabsf(__ldg(a.bias_gate + gu) - __ldg(a.bias_update + gu)) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bd = fmaxf(bd, __shfl_xor_sync(0xffffffffu, bd, o));
+      if (lane == 0) { red_s[ew] = mu; red_s[16 + ew] = bd; }
       asm volatile("bar.sync 1, %0;" ::"n"(WX_EPI_WARPS * 32) : "memory");
 #pragma unroll
-      for (int w = 0; w < WX_EPI_WARPS; ++w) mu = fmaxf(mu, red_s[w]);
+      for (int w = 0; w < WX_EPI_WARPS; ++w) { mu = fmaxf(mu, red_s[w]); bd = fmaxf(bd, red_s[16 + w]); }
       int S = 40;
       if (mu > 0.f) S = min(S, (int)floorf(log2f(30000.f / mu)));
       S = max(S, -14);
       const float scale_u = exp2f((float)S), unscale = exp2f((float)-S);
+      // e_u = e_g^2 * exp(2 (b_g - b_u)) saves one MUFU.EX2 per element: sigmoid gate, no per-unit scales, biases <= 8 apart
+      const bool one_ex2 = d.gate_nl == FGRNN_NL_SIGMOID && !a.gate_scale && !a.update_scale && bd <= 8.0f;
       for (int kb = part; kb < KH; kb += 4) {
         float uv[16];
 #pragma unroll
@@ -506,6 +522,11 @@ struct TcWxFwd {
         kc.ku = make_float2(ku, ku); kc.cu = make_float2(cu, cu);
         kc.msz = make_float2(-sz, -sz); kc.szn = make_float2(sz + sn, sz + sn);
         kc.sg = sg; kc.bg = __ldg(a.bias_gate + gu); kc.su = su; kc.bu = __ldg(a.bias_update + gu);
+        if (one_ex2) {                                   // cu becomes the ratio exp(2 (b_g - b_u)); pre >= tmin keeps e_g <= 2^30
+          const float ratio = expf(2.0f * (kc.bg - kc.bu));
+          kc.cu = make_float2(ratio, ratio);
+          kc.tmin = (30.0f - cg) / kg;
+        }
       }
       const bool tanh_gate = d.gate_nl == FGRNN_NL_TANH;
 
@@ -518,25 +539,29 @@ struct TcWxFwd {
       const uint32_t hbuf_bytes = (uint32_t)(WX_NT * 2 * L.h_tile_bytes);
       unsigned char* hop0 = sm + L.h_op + tile_off + chunk_off;
       const uint32_t hop0_remote = PAIR ? mapa_u32(smem_u32(hop0), peer) : 0u;
-      const uint32_t hready_remote = PAIR ? mapa_u32(bar(B_HREADY + es), peer) : 0u;
-      auto put_operand = [&](int buf, const uint32_t (&hi)[PAIRS], const uint32_t (&lo)[PAIRS]) {
+      const uint32_t hr_remote0 = PAIR ? mapa_u32(bar(B_HREADY + es * 2), peer) : 0u;      // partner's HREADY[es][0]; [1] is +8
+      constexpr uint32_t PEER_BYTES = 32u * NG * 2u * 16u;       // what one epilogue warp receives from its counterpart per step
+      // h (for the MMAs of step tn) -> operand tiles of buffer tn & 1, here and in the partner CTA
+      auto put_operand = [&](int tn, const uint32_t (&hi)[PAIRS], const uint32_t (&lo)[PAIRS]) {
+        const uint32_t bo = PAIR ? (uint32_t)(tn & 1) * hbuf_bytes : 0u;
+        const uint32_t rbar = hr_remote0 + (uint32_t)(tn & 1) * 8u;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           const uint4 vh = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
           const uint4 vl = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
-          const uint32_t o = (uint32_t)buf * hbuf_bytes + g * 128;
+          const uint32_t o = bo + g * 128;
           *reinterpret_cast<uint4*>(hop0 + o) = vh;
           *reinterpret_cast<uint4*>(hop0 + o + L.h_tile_bytes) = vl;
-          if (PAIR) { st_cluster_v4(hop0_remote + o, vh); st_cluster_v4(hop0_remote + o + L.h_tile_bytes, vl); }
+          if (PAIR) { st_async_v4(hop0_remote + o, vh, rbar); st_async_v4(hop0_remote + o + L.h_tile_bytes, vl, rbar); }
         }
       };
-      auto hand_off = [&]() {
-        if (PAIR) fence_proxy_async_all(); else fence_proxy_async_smem();
+      auto hand_off = [&](int tn) {
+        fence_proxy_async_smem();                          // this CTA's st.shared -> visible to its tcgen05.mma
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) { mbar_arrive_release_cluster_local(bar(B_HREADY + es)); mbar_arrive_cluster(hready_remote); }
-          else mbar_arrive(bar(B_HREADY + es));
+          if (PAIR) mbar_expect_tx(hr_bar(es, tn), PEER_BYTES);   // arrive + expect the counterpart warp's bytes
+          else mbar_arrive(hr_bar(es, tn));
         }
       };
       {
@@ -551,14 +576,10 @@ struct TcWxFwd {
         }
         put_operand(0, hi, lo);
       }
-      if (PAIR) fence_proxy_async_all(); else fence_proxy_async_smem();
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();                                   // matches the other roles' prologue barrier; weights are in TMEM
-      __syncwarp();
-      if (lane == 0) {                                   // phase 0: h_{-1} ready
-        if (PAIR) { mbar_arrive_release_cluster_local(bar(B_HREADY + es)); mbar_arrive_cluster(hready_remote); }
-        else mbar_arrive(bar(B_HREADY + es));
-      }
+      hand_off(0);                                       // phase 0: h_{-1} ready
 
       const uint32_t acc = tmem + lane_base + TM_ACC + es * TM_ACC_PER_TILE + rh * RPT;
       char* outp = a.out ? reinterpret_cast<char*>(a.out + (size_t)first_row * a.osb + gu) : nullptr;
@@ -568,75 +589,97 @@ struct TcWxFwd {
       const uint32_t zc_step = (uint32_t)d.B * HK;
       const int rows_left = d.B - first_row;
       const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
-      for (int t = 0; t < d.T; ++t) {
-        const int st = t % L.stages;
-        mbar_wait(bar(B_DFULL + es), t & 1);
-        tc_fence_after();
-        mbar_wait(bar(B_WXFULL + es * 4 + st), (t / L.stages) & 1);
-        const float* wx = reinterpret_cast<const float*>(sm + L.ring + (es * L.stages + st) * L.ring_stage_bytes) + (rh * RPT) * WX_HC + n;
-        uint32_t hi[PAIRS], lo[PAIRS];
-        float2 zq[PAIRS], cq[PAIRS];
+      // The step loop, specialised at compile time on the activation form (0: sigmoid gate, one MUFU.EX2 per element;
+      // 1: sigmoid gate, two; 2: tanh gate) and on whether z_t / c_t are stored (training forward, cu:340-341).
+      auto step_loop = [&](auto mode_tag, auto save_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        constexpr bool SAVE = decltype(save_tag)::value;
+        for (int t = 0; t < d.T; ++t) {
+          const int st = t % L.stages;
+          mbar_wait(bar(B_DFULL + es), t & 1);
+          tc_fence_after();
+          mbar_wait(bar(B_WXFULL + es * 4 + st), (t / L.stages) & 1);
+          const float* wx = reinterpret_cast<const float*>(sm + L.ring + (es * L.stages + st) * L.ring_stage_bytes) + (rh * RPT) * WX_HC + n;
+          uint32_t hi[PAIRS], lo[PAIRS];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          float va[8], vb[8], v1[8], v2[8];
-          tmem_ld8(acc + g * 8, va);
-          tmem_ld8(acc + NS + g * 8, vb);
-          tmem_ld8(acc + 2 * NS + g * 8, v1);
-          tmem_ld8(acc + 3 * NS + g * 8, v2);
-          tmem_ld_wait();
+          for (int g = 0; g < NG; ++g) {
+            float va[8], vb[8], v1[8], v2[8];
+            tmem_ld8(acc + g * 8, va);
+            tmem_ld8(acc + NS + g * 8, vb);
+            tmem_ld8(acc + 2 * NS + g * 8, v1);
+            tmem_ld8(acc + 3 * NS + g * 8, v2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int p = g * 4 + q;
-            const float2 w2 = make_float2(wx[(2 * p) * WX_HC], wx[(2 * p + 1) * WX_HC]);
-            const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
-            const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
-            const float2 pre = __ffma2_rn(tot, kc.un, w2);                       // rnn.py:289 (wComp + uComp)
-            float2 z, c;
-            if (!tanh_gate) {
-              // sigmoid gate: one MUFU.RCP serves both gates (fgrnn_tc.cu): r = 1 / ((1 + e_g)(1 + e_u))
-              float2 ag = __ffma2_rn(pre, kc.kg, kc.cg), au = __ffma2_rn(pre, kc.ku, kc.cu);
-              ag.x = fminf(ag.x, 60.0f); ag.y = fminf(ag.y, 60.0f);
-              au.x = fminf(au.x, 60.0f); au.y = fminf(au.y, 60.0f);
-              const float2 eg = make_float2(ex2_approx(ag.x), ex2_approx(ag.y)), eu = make_float2(ex2_approx(au.x), ex2_approx(au.y));
-              const float2 ga = __fadd2_rn(eg, one), ub = __fadd2_rn(eu, one);
-              const float2 ab = __fmul2_rn(ga, ub);
-              const float2 r = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
-              z = __fmul2_rn(r, ub);                                              // rnn.py:290
-              c = __ffma2_rn(__fmul2_rn(r, ga), two, mone);                       // rnn.py:292
-            } else {
-              // tanh gate: z multiplies h and crosses zero, where 2 / (1 + e) - 1 cancels; tanh_fast switches to an odd
-              // polynomial there (<= 2 ulp everywhere)
-              z = make_float2(tanh_fast(fmaf(kc.sg, pre.x, kc.bg)), tanh_fast(fmaf(kc.sg, pre.y, kc.bg)));
-              c = make_float2(tanh_fast(fmaf(kc.su, pre.x, kc.bu)), tanh_fast(fmaf(kc.su, pre.y, kc.bu)));
+            for (int q = 0; q < 4; ++q) {
+              const int p = g * 4 + q;
+              const float2 w2 = make_float2(wx[(2 * p) * WX_HC], wx[(2 * p + 1) * WX_HC]);
+              const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
+              const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
+              const float2 pre = __ffma2_rn(tot, kc.un, w2);                       // rnn.py:289 (wComp + uComp)
+              float2 z, c;
+              if (MODE < 2) {
+                // sigmoid gate: one MUFU.RCP serves both gates (fgrnn_tc.cu): r = 1 / ((1 + e_g)(1 + e_u))
+                float2 eg, eu;
+                if (MODE == 0) {
+                  const float2 pc = make_float2(fmaxf(pre.x, kc.tmin), fmaxf(pre.y, kc.tmin));
+                  const float2 ag = __ffma2_rn(pc, kc.kg, kc.cg);
+                  eg = make_float2(ex2_approx(ag.x), ex2_approx(ag.y));
+                  eu = __fmul2_rn(__fmul2_rn(eg, eg), kc.cu);
+                } else {
+                  float2 ag = __ffma2_rn(pre, kc.kg, kc.cg), au = __ffma2_rn(pre, kc.ku, kc.cu);
+                  ag.x = fminf(ag.x, 60.0f); ag.y = fminf(ag.y, 60.0f);
+                  au.x = fminf(au.x, 60.0f); au.y = fminf(au.y, 60.0f);
+                  eg = make_float2(ex2_approx(ag.x), ex2_approx(ag.y)); eu = make_float2(ex2_approx(au.x), ex2_approx(au.y));
+                }
+                const float2 ga = __fadd2_rn(eg, one), ub = __fadd2_rn(eu, one);
+                const float2 ab = __fmul2_rn(ga, ub);
+                const float2 r = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
+                z = __fmul2_rn(r, ub);                                              // rnn.py:290
+                c = __ffma2_rn(__fmul2_rn(r, ga), two, mone);                       // rnn.py:292
+              } else {
+                // tanh gate: z multiplies h and crosses zero, where 2 / (1 + e) - 1 cancels; tanh_fast switches to an odd
+                // polynomial there (<= 2 ulp everywhere)
+                z = make_float2(tanh_fast(fmaf(kc.sg, pre.x, kc.bg)), tanh_fast(fmaf(kc.sg, pre.y, kc.bg)));
+                c = make_float2(tanh_fast(fmaf(kc.su, pre.x, kc.bu)), tanh_fast(fmaf(kc.su, pre.y, kc.bu)));
+              }
+              hst[p] = __ffma2_rn(z, __ffma2_rn(kc.msz, c, hst[p]), __fmul2_rn(kc.szn, c));   // rnn.py:294-295
+              if (SAVE) {
+                const int rj = 2 * p;
+                if (rj < rows_left) { zp[rj * HK] = z.x; cp[rj * HK] = c.x; }
+                if (rj + 1 < rows_left) { zp[(rj + 1) * HK] = z.y; cp[(rj + 1) * HK] = c.y; }
+              }
+              const __half2 hh = __float22half2_rn(hst[p]);
+              const float2 hf = __half22float2(hh);
+              const __half2 hl = __float22half2_rn(__fadd2_rn(hst[p], make_float2(-hf.x, -hf.y)));
+              hi[p] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[p] = *reinterpret_cast<const uint32_t*>(&hl);
             }
-            hst[p] = __ffma2_rn(z, __ffma2_rn(kc.msz, c, hst[p]), __fmul2_rn(kc.szn, c));   // rnn.py:294-295
-            zq[p] = z; cq[p] = c;
-            const __half2 hh = __float22half2_rn(hst[p]);
-            const float2 hf = __half22float2(hh);
-            const __half2 hl = __float22half2_rn(__fadd2_rn(hst[p], make_float2(-hf.x, -hf.y)));
-            hi[p] = *reinterpret_cast<const uint32_t*>(&hh);
-            lo[p] = *reinterpret_cast<const uint32_t*>(&hl);
           }
-        }
-        put_operand(PAIR ? ((t + 1) & 1) : 0, hi, lo);
-        hand_off();
-        if (lane == 0) mbar_arrive(bar(B_WXEMPTY + es * 4 + st));
-        if (outp) {
+          if (t + 1 < d.T) {                                 // nobody reads h_{T-1} as an operand (and no store may be in flight
+            put_operand(t + 1, hi, lo);                      // towards the partner when the pair leaves the kernel)
+            hand_off(t + 1);
+          }
+          if (lane == 0) mbar_arrive(bar(B_WXEMPTY + es * 4 + st));
+          if (outp) {
 #pragma unroll
-          for (int q = 0; q < PAIRS; ++q) {
-            if (2 * q < rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
-            if (2 * q + 1 < rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
+            for (int q = 0; q < PAIRS; ++q) {
+              if (2 * q < rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
+              if (2 * q + 1 < rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
+            }
+            outp += step_bytes;
           }
-          outp += step_bytes;
+          if (SAVE) { zp += zc_step; cp += zc_step; }
         }
-        if (zp) {
-#pragma unroll
-          for (int q = 0; q < PAIRS; ++q) {
-            if (2 * q < rows_left) { zp[(2 * q) * HK] = zq[q].x; cp[(2 * q) * HK] = cq[q].x; }
-            if (2 * q + 1 < rows_left) { zp[(2 * q + 1) * HK] = zq[q].y; cp[(2 * q + 1) * HK] = cq[q].y; }
-          }
-          zp += zc_step; cp += zc_step;
-        }
+      };
+      using I0 = IntTag<0>; using I1 = IntTag<1>; using I2 = IntTag<2>; using BF = BoolTag<false>; using BT = BoolTag<true>;
+      const int mode = tanh_gate ? 2 : (one_ex2 ? 0 : 1);
+      switch (mode * 2 + (zp ? 1 : 0)) {
+        case 0: step_loop(I0{}, BF{}); break;
+        case 1: step_loop(I0{}, BT{}); break;
+        case 2: step_loop(I1{}, BF{}); break;
+        case 3: step_loop(I1{}, BT{}); break;
+        case 4: step_loop(I2{}, BF{}); break;
+        default: step_loop(I2{}, BT{}); break;
       }
       if (a.h_last) {
 #pragma unroll
