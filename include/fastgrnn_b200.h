@@ -170,6 +170,14 @@ FGRNN_API int fgrnn_abi_version(void);
 /* Cumulative number of kernels this library has launched in this process. */
 FGRNN_API uint64_t fgrnn_launch_count(void);
 
+/* Layout ingest for the reference trainer's native batches: x[b][f][t] by element strides (the loaders yield (B,F,T)
+   with T innermost; trainClassifier.py:203-204 only permutes the VIEW) -> dst [B][T][F] contiguous fp32, one pass at
+   HBM speed (32 x 32 tiles through shared memory).  The recurrence then reads dst with (stride_b, stride_t) = (T*F, F).
+   mean / std (optional, [F] each, both or neither): the loaders' per-feature standardisation (x - mean) / std of
+   preprocessing.py:60-76 applied on the way, with the reference's two correctly rounded operations. */
+FGRNN_API int fgrnn_ingest_bft(const float* src, int64_t stride_b, int64_t stride_f, int64_t stride_t, float* dst,
+                               const float* mean, const float* stdev, int32_t B, int32_t F, int32_t T, int32_t device, void* stream);
+
 /* Diagnostic (tests only): fill every SM's tensor memory and shared memory with a NaN pattern, enqueued on
    `stream`, so that the next launch cannot be saved by operands a predecessor left on chip.  The reference
    has no counterpart; the first-launch parity tests call it between launches. */

@@ -83,6 +83,8 @@ SYMBOLS = {
     "fgrnn_abi_version": (C.c_int, []),
     "fgrnn_launch_count": (C.c_uint64, []),
     "fgrnn_debug_poison_onchip": (C.c_int, [C.c_int, C.c_void_p]),
+    "fgrnn_ingest_bft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

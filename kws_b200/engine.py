@@ -66,7 +66,10 @@ class _Problem:
         if x.dtype not in (torch.float32, torch.bfloat16):
             raise RuntimeError("input must be float32 or bfloat16, got %s" % x.dtype)
         if x.stride(2) != 1 and x.shape[2] > 1:
-            x = x.contiguous()
+            # features are not contiguous: the trainer's `audio.permute(2, 0, 1)` view of a (B,F,T) batch
+            # (trainClassifier.py:203-204) and its relatives.  One tiled pass through the ingest kernel puts it into
+            # (B,T,F); the result is a batch-first tensor, viewed back to the caller's dimension order without a copy.
+            x = ingest_features_last(x, batch_first)
         self.x = x
         self.device = x.device
         self.batch_first = bool(batch_first)
@@ -128,6 +131,68 @@ class _Problem:
         p.h0 = _ptr(self.h0)
         p.gate_scale = _ptr(self.t.get("gate_scale"))
         p.update_scale = _ptr(self.t.get("update_scale"))
+
+
+def ingest_features_last(x: torch.Tensor, batch_first: bool, mean: Optional[torch.Tensor] = None,
+                         std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,B,F] (or [B,T,F]) with any strides -> a tensor of the same shape whose feature stride is 1, produced by
+    ``fgrnn_ingest_bft`` (fp32) in one pass at HBM speed; other dtypes fall back to ``contiguous()``.  With ``mean`` /
+    ``std`` (F values each, e.g. the loaders' (1,F,1) arrays) the pass also applies ``(x - mean) / std``
+    (preprocessing.py:76) with the reference's rounding, so raw features can be fed."""
+    norm = mean is not None
+    if norm:
+        mean = mean.reshape(-1).to(x.device, torch.float32).contiguous()
+        std = std.reshape(-1).to(x.device, torch.float32).contiguous()
+        if mean.numel() != x.shape[2] or std.numel() != x.shape[2]:
+            raise RuntimeError("mean / std must have %d entries" % x.shape[2])
+    if x.dtype != torch.float32 or not x.is_cuda or x.numel() == 0:
+        if norm:
+            x = (x.float() - mean) / std
+        return x.contiguous()
+    lib = _lib.load()
+    B, T = (x.shape[0], x.shape[1]) if batch_first else (x.shape[1], x.shape[0])
+    F = x.shape[2]
+    sb, st = (x.stride(0), x.stride(1)) if batch_first else (x.stride(1), x.stride(0))
+    if B > 65535:
+        return ((x - mean) / std).contiguous() if norm else x.contiguous()
+    dst = torch.empty((B, T, F), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.fgrnn_ingest_bft(x.data_ptr(), sb, x.stride(2), st, dst.data_ptr(),
+                                        mean.data_ptr() if norm else None, std.data_ptr() if norm else None, B, F, T,
+                                        x.device.index if x.device.index is not None else torch.cuda.current_device(),
+                                        _stream(x.device)), "fastgrnn ingest")
+    return dst if batch_first else dst.transpose(0, 1)
+
+
+def fold_input_normalization(params: Dict[str, torch.Tensor], mean: torch.Tensor, std: torch.Tensor, *,
+                             layout: str = "IH") -> Dict[str, torch.Tensor]:
+    """Fold the loaders' per-feature standardisation ``(x - mean) / std`` (data_pipeline/preprocessing.py:60-76; mean /
+    std of shape (1,F,1), ``model_batchnorm/mean.npy``) into the first layer, so that RAW features can be fed:
+
+        ((x - m) / s) . W  =  x . (diag(1/s) W)  -  (m / s) . W
+
+    i.e. the rows of W (W1 for a low-rank layer) are divided by std and both biases absorb ``-(mean/std) . W``.
+    Returns a new parameter dict (same keys, same layout); the inputs are not modified."""
+    ih = layout == "IH"
+    m = mean.reshape(-1).to(params["bias_gate"])
+    s = std.reshape(-1).to(params["bias_gate"])
+    out = dict(params)
+    with torch.no_grad():
+        inv = 1.0 / s
+        if _present(params.get("W")):
+            W = params["W"] if ih else params["W"].t()                    # [I,H]
+            shift = -((m * inv).unsqueeze(0) @ W)                         # [1,H]
+            Wn = W * inv.unsqueeze(1)
+            out["W"] = (Wn if ih else Wn.t()).contiguous()
+        else:
+            W1 = params["W1"] if ih else params["W1"].t()                 # [I,r]
+            W2 = params["W2"] if ih else params["W2"].t()                 # [r,H]
+            shift = -(((m * inv).unsqueeze(0) @ W1) @ W2)
+            W1n = W1 * inv.unsqueeze(1)
+            out["W1"] = (W1n if ih else W1n.t()).contiguous()
+        out["bias_gate"] = (params["bias_gate"] + shift).contiguous()
+        out["bias_update"] = (params["bias_update"] + shift).contiguous()
+    return out
 
 
 def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:

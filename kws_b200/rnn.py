@@ -12,7 +12,7 @@ Mirrored reference symbols (file:line in /root/reference):
   FastGRNNCUDACell rnn.py:454-549 | BaseRNN rnn.py:551-668 | FastGRNN rnn.py:670-707
   FastGRNNCUDA rnn.py:738-889 | FastGRNNFunction rnn.py:891-905
   FastGRNNUnrollFunction rnn.py:907-972 | onnx_exportable_rnn rnn.py:19-38
-  FastGRNNBatchNorm rnn.py:709-734 (name importable for model.py:6; out of scope)
+  FastGRNNBatchNormCell rnn.py:316-452 | FastGRNNBatchNorm rnn.py:709-734 (eval mode folded into the recurrence)
 
 There is no CPU path: parameters/inputs must live on a CUDA device, otherwise the
 forward raises ``RuntimeError``.  Reference call-site defects that this module
@@ -30,7 +30,7 @@ from . import engine, fastgrnn_cuda, ref_utils
 from . import ref_utils as utils   # the reference module refers to ``utils.findCUDA`` (rnn.py:476)
 
 __all__ = ["gen_nonlinearity", "RNNCell", "FastGRNNCell", "FastGRNNCUDACell", "BaseRNN", "FastGRNN",
-           "FastGRNNCUDA", "FastGRNNBatchNorm", "FastGRNNFunction", "FastGRNNUnrollFunction",
+           "FastGRNNCUDA", "FastGRNNBatchNorm", "FastGRNNBatchNormCell", "FastGRNNFunction", "FastGRNNUnrollFunction",
            "onnx_exportable_rnn", "fastgrnn_cuda"]
 
 NON_LINEARITY = {"sigmoid": 0, "relu": 1, "tanh": 2}                      # rnn.py:478, rnn.py:751
@@ -453,7 +453,8 @@ class BaseRNN(nn.Module):
             # overwritten below and must not alias what autograd saved
             return None if hiddenState is None else hiddenState[d].to(dev, torch.float32).clone().contiguous()
 
-        out = cell.unroll(input, h0_of(0), self._batch_first)
+        kw = {"training": training} if isinstance(cell, FastGRNNBatchNormCell) else {}
+        out = cell.unroll(input, h0_of(0), self._batch_first, **kw)
         outs = [out]
         if self._bidirectional:
             # the reverse direction consumes input[T-1-i] at step i and stores its state at index i
@@ -503,15 +504,113 @@ class FastGRNN(nn.Module):
         return self
 
 
-class FastGRNNBatchNorm(nn.Module):
-    """rnn.py:709-734.  Importable because ``model.py:6`` imports the name; the BatchNorm variant is
-    different math (per-step batch statistics, rnn.py:316-452) and outside this engine's scope
-    (SURVEY.md section 8f, rank 3)."""
+class FastGRNNBatchNormCell(FastGRNNCell):
+    """rnn.py:316-452: FastGRNN cell with four ``nn.BatchNorm1d`` layers -- on W x (``bn_w``), on U h (``bn_u``) and on the
+    two pre-activations (``bn_gate``, ``bn_update``).  Same parameter names / creation order as the reference, so its
+    checkpoints (``model_batchnorm/FastGRNNBatchNorm_KeywordSpotter.pt``-shaped state_dicts) load.
 
-    def __init__(self, *args, **kwargs):
+    EVAL MODE runs on the engine: with running statistics every BatchNorm layer is a per-unit affine map
+    ``a*v + b`` (a = weight/sqrt(var+eps), b = bias - mean*a), so
+
+        pre       = x.(W diag(a_w)) + h.(U diag(a_u))                      columns of W / U scaled
+        z         = gate  (a_g * pre + [a_g (b_w + b_u + bias_gate)   + b_g])
+        c         = update(a_c * pre + [a_c (b_w + b_u + bias_update) + b_c])
+
+    i.e. the plain recurrence with folded weights, folded biases and the per-unit ``gate_scale`` / ``update_scale`` of the
+    C ABI.  Training mode (per-time-step BATCH statistics, rnn.py:395-405 with ``training=True``) is a different
+    computation -- a cross-batch reduction inside every step -- and is not accelerated: it raises."""
+
+    def __init__(self, input_size, hidden_size, gate_nonlinearity="sigmoid", update_nonlinearity="tanh",
+                 wRank=None, uRank=None, wSparsity=1.0, uSparsity=1.0, zetaInit=1.0, nuInit=-4.0,
+                 name="FastGRNNBatchNorm"):
+        super(FastGRNNBatchNormCell, self).__init__(input_size, hidden_size, gate_nonlinearity, update_nonlinearity,
+                                                    wRank, uRank, wSparsity, uSparsity, zetaInit, nuInit, name)
+        self.bn_w = nn.BatchNorm1d(hidden_size)                          # rnn.py:363-366
+        self.bn_u = nn.BatchNorm1d(hidden_size)
+        self.bn_gate = nn.BatchNorm1d(hidden_size)
+        self.bn_update = nn.BatchNorm1d(hidden_size)
+
+    @property
+    def cellType(self):
+        return "FastGRNNBatchNorm"
+
+    @staticmethod
+    def _affine(bn):
+        a = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        return a, bn.bias.detach().float() - bn.running_mean.float() * a
+
+    def folded_params(self):
+        """The eval-mode cell as plain FastGRNN parameters + pre-activation scales (all on the cell's device)."""
+        with torch.no_grad():
+            aw, bw = self._affine(self.bn_w)
+            au, bu = self._affine(self.bn_u)
+            ag, bg = self._affine(self.bn_gate)
+            ac, bc = self._affine(self.bn_update)
+            p = {}
+            if self._wRank is None:
+                p["W"] = (self.W.detach() * aw).contiguous()
+            else:
+                p["W1"] = self.W1.detach().contiguous(); p["W2"] = (self.W2.detach() * aw).contiguous()
+            if self._uRank is None:
+                p["U"] = (self.U.detach() * au).contiguous()
+            else:
+                p["U1"] = self.U1.detach().contiguous(); p["U2"] = (self.U2.detach() * au).contiguous()
+            shift = bw + bu
+            p["bias_gate"] = (ag * (shift + self.bias_gate.detach()[0]) + bg).unsqueeze(0).contiguous()
+            p["bias_update"] = (ac * (shift + self.bias_update.detach()[0]) + bc).unsqueeze(0).contiguous()
+            p["gate_scale"] = ag.unsqueeze(0).contiguous()
+            p["update_scale"] = ac.unsqueeze(0).contiguous()
+            p["zeta"] = self.zeta.detach().contiguous(); p["nu"] = self.nu.detach().contiguous()
+        return p
+
+    def _eval_mode(self, training):
+        # the reference picks eval statistics when called with training=False (``self.bn_w.eval()(wComp)``) and otherwise
+        # follows the BatchNorm modules' own mode (rnn.py:395-396)
+        return (not training) or not (self.bn_w.training or self.bn_u.training or self.bn_gate.training or self.bn_update.training)
+
+    def unroll(self, input, h0, batch_first, training=True):
+        device = self._device()
+        _require_cuda(device, "FastGRNNBatchNorm.forward")
+        if not self._eval_mode(training):
+            raise NotImplementedError("FastGRNNBatchNorm in training mode normalises every time step with BATCH statistics "
+                                      "(rnn.py:395-405), which this engine does not accelerate; call with training=False "
+                                      "or put the module in eval() mode (running statistics fold into the recurrence)")
+        if not training:
+            for bn in (self.bn_w, self.bn_u, self.bn_gate, self.bn_update):
+                bn.eval()                                                # the reference's ``self.bn_w.eval()(...)`` has the same side effect
+        out, _, _, _ = engine.forward(input.to(device), self.folded_params(), h0, layout="IH", batch_first=batch_first,
+                                      gate_nl=self._gate_nonlinearity, update_nl=self._update_nonlinearity)
+        return out
+
+    def forward(self, input, state, training=True):
+        """One step (rnn.py:377-410): input [B,I], state [B,H] -> new_h [B,H]."""
+        device = self._device()
+        return self.unroll(input.to(device).unsqueeze(0), state.to(device).contiguous(), False, training=training)[0]
+
+
+class FastGRNNBatchNorm(nn.Module):
+    """rnn.py:709-734: "FastGRNN with Batch Normalization wrapper class".  ``forward(input, hiddenState=None,
+    training=True)``; eval mode is accelerated (see FastGRNNBatchNormCell), training mode raises."""
+
+    def __init__(self, input_size, hidden_size, gate_nonlinearity="sigmoid", update_nonlinearity="tanh",
+                 wRank=None, uRank=None, wSparsity=1.0, uSparsity=1.0, zetaInit=1.0, nuInit=-4.0, batch_first=False):
         super(FastGRNNBatchNorm, self).__init__()
-        raise NotImplementedError("FastGRNNBatchNorm is outside the kws_b200 hot-path scope "
-                                  "(SURVEY.md 8f rank 3); use FastGRNN / FastGRNNCUDA")
+        self.cell = FastGRNNBatchNormCell(input_size, hidden_size, gate_nonlinearity=gate_nonlinearity,
+                                          update_nonlinearity=update_nonlinearity, wRank=wRank, uRank=uRank,
+                                          wSparsity=wSparsity, uSparsity=uSparsity, zetaInit=zetaInit, nuInit=nuInit)
+        self.unrollRNN = BaseRNN(self.cell, batch_first=batch_first)
+        self.training = True
+
+    def getVars(self):
+        return self.unrollRNN.getVars()
+
+    def forward(self, input, hiddenState=None, training=True):
+        return self.unrollRNN(input, hiddenState, training=training)
+
+    def train(self, mode=True):
+        self.training = mode
+        super(FastGRNNBatchNorm, self).train(mode)
+        return self
 
 
 class FastGRNNCUDA(nn.Module):

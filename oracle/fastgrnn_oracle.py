@@ -128,6 +128,50 @@ def cell_step(x: torch.Tensor, h: torch.Tensor, p: Params,
     return new_h
 
 
+def bn_eval(a: torch.Tensor, bn: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """``nn.BatchNorm1d`` in eval mode on a [B,H] tensor (what ``self.bn_w.eval()(wComp)`` computes, rnn.py:395):
+    running statistics, affine weight / bias.  ``bn`` = dict(weight, bias, mean, var, eps)."""
+    return torch.nn.functional.batch_norm(a, bn["mean"], bn["var"], bn["weight"], bn["bias"], False, 0.0, float(bn["eps"]))
+
+
+def cell_step_bn(x: torch.Tensor, h: torch.Tensor, p: Params, bns: Dict[str, Dict[str, torch.Tensor]],
+                 gate_nl: str = "sigmoid", update_nl: str = "tanh") -> torch.Tensor:
+    """One step of ``FastGRNNBatchNormCell.forward`` with ``training=False`` (rnn.py:377-410).
+    ``bns`` has the four layers "w", "u", "gate", "update" (rnn.py:363-366)."""
+    if p.W is not None:
+        wComp = torch.matmul(x, p.W)                                     # rnn.py:385
+    else:
+        wComp = torch.matmul(torch.matmul(x, p.W1), p.W2)                # rnn.py:387
+    if p.U is not None:
+        uComp = torch.matmul(h, p.U)                                     # rnn.py:391
+    else:
+        uComp = torch.matmul(torch.matmul(h, p.U1), p.U2)                # rnn.py:393
+    wComp = bn_eval(wComp, bns["w"])                                     # rnn.py:396
+    uComp = bn_eval(uComp, bns["u"])                                     # rnn.py:397
+    pre_gate = wComp + uComp + p.bias_gate                               # rnn.py:400
+    pre_update = wComp + uComp + p.bias_update                           # rnn.py:401
+    pre_gate = bn_eval(pre_gate, bns["gate"])                            # rnn.py:404
+    pre_update = bn_eval(pre_update, bns["update"])                      # rnn.py:405
+    z = nonlinearity(pre_gate, gate_nl)                                  # rnn.py:408
+    c = nonlinearity(pre_update, update_nl)                              # rnn.py:409
+    return z * h + (torch.sigmoid(p.zeta) * (1.0 - z) + torch.sigmoid(p.nu)) * c      # rnn.py:412-413
+
+
+def unroll_bn(x: torch.Tensor, p: Params, bns, h0: Optional[torch.Tensor] = None, batch_first: bool = False,
+              gate_nl: str = "sigmoid", update_nl: str = "tanh") -> torch.Tensor:
+    """All T hidden states of the eval-mode BatchNorm variant (``FastGRNNBatchNorm`` -> ``BaseRNN.forward``,
+    rnn.py:709-734, :620-622 / :658-660), dtype-generic.  h0 is [B,H]."""
+    xs = x.transpose(0, 1) if batch_first else x
+    T, B = xs.shape[0], xs.shape[1]
+    h = torch.zeros(B, p.hidden_size, dtype=x.dtype) if h0 is None else h0
+    outs = []
+    for t in range(T):
+        h = cell_step_bn(xs[t], h, p, bns, gate_nl, update_nl)
+        outs.append(h)
+    out = torch.stack(outs, 0)
+    return out.transpose(0, 1) if batch_first else out
+
+
 def unroll(x: torch.Tensor, p: Params, h0: Optional[torch.Tensor] = None,
            batch_first: bool = False, gate_nl: str = "sigmoid",
            update_nl: str = "tanh") -> torch.Tensor:

@@ -36,7 +36,8 @@ def load_golden(name):
 
 
 def golden_case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("model_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith("model_") and not f.startswith("bn_"))
 
 
 def golden_model_names():

@@ -84,8 +84,9 @@ def test_no_cpu_fallback_and_gpu_only_modules():
             krnn.FastGRNNCUDA(8, 16)
         with pytest.raises(Exception, match="FastGRNNCUDA is supported only on GPU devices."):   # rnn.py:476-477
             krnn.FastGRNNCUDACell(8, 16)
-    with pytest.raises(NotImplementedError):
-        krnn.FastGRNNBatchNorm(8, 16)
+    bn = krnn.FastGRNNBatchNorm(8, 16)                       # constructs on the CPU like the reference; runs on CUDA only
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bn(torch.randn(3, 2, 8), training=False)
     with pytest.raises(RuntimeError, match="input must be a CUDA tensor"):                       # cpp:69
         e = torch.empty(0)
         ext.forward_unroll(torch.randn(3, 2, 8), torch.randn(16, 8), torch.randn(16, 16), torch.ones(1, 16),
