@@ -61,7 +61,7 @@ struct XwArgs {
   float* wx;                       // [T][B][H] contiguous
   int KI;                          // I rounded up to a multiple of 16 (<= 256)
   int KSW;                         // k width of a slab's operand tile: min(KI, 64)
-  int BOXI;                        // features per TMA box: min(I, 64)
+  int BOXI;                        // features per TMA box = row pitch of the raw tile: I (one box per 16-row group and tile)
   int nslab;                       // ceil(KI / 64)
   int x_time_outer;
   int ntiles, nrb;                 // tiles = T * nrb, nrb = ceil(B / 64)
@@ -71,17 +71,18 @@ constexpr int XW_NS = 32, XW_ROWS = XW_NS * WX_NT;       // 64 rows of one time 
 constexpr int XW_CONV_WARPS = 4, XW_CONV_ROWS = XW_ROWS / XW_CONV_WARPS;
 constexpr int XW_MMA_WARPS = 2;                           // role 0: lo products -> C, role 1: hi.hi -> M
 constexpr int XW_THREADS = 32 * (WX_EPI_WARPS + XW_CONV_WARPS + XW_MMA_WARPS);
-constexpr int XW_XBUF = 4, XW_RAW_STAGES = 4;
+constexpr int XW_XBUF = 4;
+__host__ __device__ inline int xw_raw_stages(int nslab) { return nslab > 1 ? 2 : 4; }      // raw tiles in flight per converter warp
 constexpr int XW_TM_ACC = 256;                            // W_hi | W_lo take up to 2 x 128 columns (KI <= 256)
 
 struct XwSmem { int x_op, raw, bars, misc, total; int x_tile_bytes, raw_stage_bytes; };
-__host__ __device__ inline XwSmem xw_smem_layout(int BOXI, int KSW, int esz) {
+__host__ __device__ inline XwSmem xw_smem_layout(int BOXI, int KSW, int esz, int nslab) {
   XwSmem L;
   L.x_tile_bytes = XW_NS * KSW * 2;
   L.raw_stage_bytes = XW_CONV_ROWS * BOXI * esz;
   L.x_op = 0;                                                     // [XBUF][NT][hi|lo][x_tile_bytes]
   L.raw = (XW_XBUF * WX_NT * 2 * L.x_tile_bytes + 127) & ~127;    // [CONV_WARPS][RAW_STAGES][raw_stage_bytes]
-  L.bars = (L.raw + XW_CONV_WARPS * XW_RAW_STAGES * L.raw_stage_bytes + 15) & ~15;
+  L.bars = (L.raw + XW_CONV_WARPS * xw_raw_stages(nslab) * L.raw_stage_bytes + 15) & ~15;
   L.misc = L.bars + 32 * 8;
   L.total = L.misc + 128;
   return L;
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
   const Dims d = a.d;
   const int I = d.I, KI = a.KI, H = d.H;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
-  const XwSmem L = xw_smem_layout(a.BOXI, a.KSW, esz);
+  const XwSmem L = xw_smem_layout(a.BOXI, a.KSW, esz, a.nslab);
+  const int RS = xw_raw_stages(a.nslab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
   float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
   if (tid == 0) {
     for (int s = 0; s < 2 * WX_NT; ++s) { mbar_init(bar(B_DEMPTY + s), WX_EPI_WARPS / WX_NT); mbar_init(bar(B_DFULL + s), XW_MMA_WARPS); }
     for (int b = 0; b < XW_XBUF; ++b) { mbar_init(bar(B_XFULL + b), XW_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), XW_MMA_WARPS); }
-    for (int st = 0; st < XW_CONV_WARPS * XW_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
+    for (int st = 0; st < XW_CONV_WARPS * 4; ++st) mbar_init(bar(B_RAWFULL + st), 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -167,29 +169,30 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
     // =========================== x path: TMA -> fp16 hi/lo split -> K-major operand tiles =============
     const int cw = warp - W_CONV0;
     const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
-    unsigned char* raw_base = sm + L.raw + cw * XW_RAW_STAGES * L.raw_stage_bytes;
-    auto issue_tma = [&](int u) {
-      const int j = u / nslab, sl = u - j * nslab;
+    unsigned char* raw_base = sm + L.raw + cw * RS * L.raw_stage_bytes;
+    // one TMA box per tile and converter warp: 16 rows x ALL I features (1 KB contiguous per row at I = 256; the first
+    // version fetched 64-feature slabs, 256-byte pieces of rows 101 KB apart, and read HBM at 2.6 TB/s)
+    auto issue_tma = [&](int j) {
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
       const int t = tile / a.nrb, r0 = (tile - t * a.nrb) * XW_ROWS + cw * XW_CONV_ROWS;
-      const int st = u % XW_RAW_STAGES;
-      const uint32_t fb = bar(B_RAWFULL + cw * XW_RAW_STAGES + st);
+      const int st = j % RS;
+      const uint32_t fb = bar(B_RAWFULL + cw * 4 + st);
       mbar_expect_tx(fb, raw_bytes);
-      if (a.x_time_outer) tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, sl * 64, r0, t, fb);
-      else tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, sl * 64, t, r0, fb);
+      if (a.x_time_outer) tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, r0, t, fb);
+      else tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, t, r0, fb);
     };
     if (lane == 0)
-      for (int u = 0; u < XW_RAW_STAGES && u < my_units; ++u) issue_tma(u);
+      for (int j = 0; j < RS && j < my_tiles; ++j) issue_tma(j);
     tc_fence_before();
     __syncthreads();
     // 16 rows x 8 chunks of 8 features = 128 tasks per slab, 4 per lane
     const int nch_slab = a.KSW >> 3, boxi = a.BOXI;
     const uint32_t xbuf_bytes = (uint32_t)(WX_NT * 2 * L.x_tile_bytes);
     for (int u = 0; u < my_units; ++u) {
-      const int st = u % XW_RAW_STAGES, xb = u % XW_XBUF;
-      const int sl = u % nslab;
+      const int xb = u % XW_XBUF;
+      const int j = u / nslab, sl = u - j * nslab, st = j % RS;
       const int nch_here = min(nch_slab, (KI >> 3) - sl * 8);          // chunks of this slab that exist in K
-      mbar_wait(bar(B_RAWFULL + cw * XW_RAW_STAGES + st), (u / XW_RAW_STAGES) & 1);
+      if (sl == 0) mbar_wait(bar(B_RAWFULL + cw * 4 + st), (j / RS) & 1);
       mbar_wait(bar(B_XEMPTY + xb), ((u / XW_XBUF) & 1) ^ 1);
       const unsigned char* raw = raw_base + st * L.raw_stage_bytes;
       unsigned char* xdst = sm + L.x_op + xb * xbuf_bytes;
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
         const int jj = lane & 7, row = (it & 1) * 8 + jj, ch = (jj + (lane >> 3) + 4 * (it >> 1)) & 7;
         if (ch < nch_slab) {
           float v[8];
-          if (ch < nch_here && ch * 8 < boxi) {           // inside the TMA box (features past I are zero-filled by the TMA unit)
-            const unsigned char* src = raw + (size_t)row * boxi * esz + ch * 8 * esz;
+          if (ch < nch_here && (sl * 8 + ch) * 8 < boxi) {           // inside the row (K padding chunks are zeros)
+            const unsigned char* src = raw + (size_t)row * boxi * esz + (sl * 8 + ch) * 8 * esz;
             if (esz == 4) {
               const int sw = (jj >> 2) & 1;
               const float4 pa = *reinterpret_cast<const float4*>(src + sw * 16), pb = *reinterpret_cast<const float4*>(src + (sw ^ 1) * 16);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(XW_THREADS, 1) tc_xw_kernel(const XwArgs a, co
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(B_XFULL + xb));
-        if (u + XW_RAW_STAGES < my_units) issue_tma(u + XW_RAW_STAGES);
+        if (sl == nslab - 1 && j + RS < my_tiles) issue_tma(j + RS);       // this warp is done with the raw tile of tile j
       }
       __syncwarp();
     }
@@ -751,7 +754,7 @@ int launch_tc_wide_fwd(const SmemFwdArgs& s, const float* gate_scale, const floa
   xa.d = d; xa.layout = s.layout; xa.W = s.W; xa.wx = wx_ws;
   xa.KI = (d.I + 15) & ~15;
   xa.KSW = xa.KI < 64 ? xa.KI : 64;
-  xa.BOXI = d.I < 64 ? d.I : 64;
+  xa.BOXI = d.I;
   xa.nslab = (xa.KI + 63) / 64;
   xa.nrb = (d.B + XW_ROWS - 1) / XW_ROWS;
   xa.ntiles = d.T * xa.nrb;
@@ -759,7 +762,7 @@ int launch_tc_wide_fwd(const SmemFwdArgs& s, const float* gate_scale, const floa
   int rc = make_row_tile_map(&xmap, s.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, s.xsb, s.xst, XW_CONV_ROWS, &xa.x_time_outer, xa.BOXI);
   if (rc) return rc;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
-  const XwSmem XL = xw_smem_layout(xa.BOXI, xa.KSW, esz);
+  const XwSmem XL = xw_smem_layout(xa.BOXI, xa.KSW, esz, xa.nslab);
   FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_xw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XL.total));
   const int hy = d.H / WX_HC;
   int gx = xa.ntiles < 148 * 4 / hy ? xa.ntiles : 148 / hy;           // persistent: one CTA per SM over both unit halves
