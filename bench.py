@@ -126,9 +126,9 @@ class ClockSampler:
                     reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
                 except Exception:                 # noqa: BLE001 -- older bindings
                     reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                    self.samples.append((mhz, power, reasons))
-            except Exception:                     # noqa: BLE001
-                pass
+                self.samples.append((mhz, power, reasons))
+            except Exception as e:                # noqa: BLE001 -- keep polling, remember why a poll failed
+                self.error = "%s: %s" % (type(e).__name__, e)
             time.sleep(0.0001)
 
     def begin(self, timeout=0.5):
@@ -146,7 +146,7 @@ class ClockSampler:
             self._thread.join(timeout=2)
             self.samples = self.samples[getattr(self, "_skip", 0):]
             if not self.samples:
-                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "error": getattr(self, "error", None)}
             mask = 0
             for _, _, r in self.samples:
                 mask |= r

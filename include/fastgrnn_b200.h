@@ -178,6 +178,11 @@ FGRNN_API uint64_t fgrnn_launch_count(void);
 FGRNN_API int fgrnn_ingest_bft(const float* src, int64_t stride_b, int64_t stride_f, int64_t stride_t, float* dst,
                                const float* mean, const float* stdev, int32_t B, int32_t F, int32_t T, int32_t device, void* stream);
 
+/* Tuning / test override of the launchers' tile configuration.  Keys are the names of the environment variables that set
+   the same values at process start (FGRNN_TC_NS, FGRNN_TC_NT, FGRNN_TC_BR_NS, FGRNN_TC_WIDE, FGRNN_FAST_NL,
+   FGRNN_SMEM_CFG); the environment is read once, not on the launch path.  value NULL or "" clears the override. */
+FGRNN_API int fgrnn_debug_set_tuning(const char* name, const char* value);
+
 /* Diagnostic (tests only): fill every SM's tensor memory and shared memory with a NaN pattern, enqueued on
    `stream`, so that the next launch cannot be saved by operands a predecessor left on chip.  The reference
    has no counterpart; the first-launch parity tests call it between launches. */

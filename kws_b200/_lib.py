@@ -83,6 +83,7 @@ SYMBOLS = {
     "fgrnn_abi_version": (C.c_int, []),
     "fgrnn_launch_count": (C.c_uint64, []),
     "fgrnn_debug_poison_onchip": (C.c_int, [C.c_int, C.c_void_p]),
+    "fgrnn_debug_set_tuning": (C.c_int, [C.c_char_p, C.c_char_p]),
     "fgrnn_ingest_bft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -140,6 +141,11 @@ def check(rc: int, what: str) -> None:
     msg = lib.fgrnn_strerror(rc).decode()
     detail = lib.fgrnn_last_error_detail().decode()
     raise RuntimeError("%s: %s%s" % (what, msg, (": " + detail) if detail else ""))
+
+
+def set_tuning(name: str, value=None) -> None:
+    """Override a launcher tuning key (``FGRNN_TC_NS`` ...; the environment only sets the process-start default)."""
+    check(load().fgrnn_debug_set_tuning(name.encode(), None if value is None else str(value).encode()), "set_tuning")
 
 
 def launch_count() -> int:

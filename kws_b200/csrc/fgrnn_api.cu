@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "fgrnn_kernels.cuh"
 
@@ -20,6 +21,23 @@ void set_error_detail(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG"};
+static std::atomic<int> g_tune[TUNE_COUNT];
+static std::once_flag g_tune_once;
+static int tune_parse(int key, const char* e) {
+  if (key == TUNE_SMEM_CFG) return e[0] == 'A' && e[1] == '7' ? '7' : e[0];       // 'A' | 'A7' | 'B' | 'C'
+  return atoi(e);
+}
+static void tune_init() {
+  std::call_once(g_tune_once, [] {
+    for (int k = 0; k < TUNE_COUNT; ++k) {
+      const char* e = getenv(kTuneNames[k]);
+      g_tune[k].store(e && e[0] ? tune_parse(k, e) : TUNE_UNSET);
+    }
+  });
+}
+int tuning(TuneKey key) { tune_init(); return g_tune[key].load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -153,8 +171,8 @@ FwdPlan plan_forward(const FgrnnForward& f, void* ws) {
   pl.path = select_fwd_path(f);
   Carver cv(ws);
   pl.tc_wide = pl.path == FGRNN_PATH_TCGEN05 && !tc_fwd_ok(f);
-  if (pl.path == FGRNN_PATH_TCGEN05 && !pl.tc_wide && tc_wide_ok(f))
-    if (const char* e = getenv("FGRNN_TC_WIDE")) pl.tc_wide = atoi(e) != 0;      // tests: hoisted kernels on a shape the fused kernel covers
+  if (pl.path == FGRNN_PATH_TCGEN05 && !pl.tc_wide && tc_wide_ok(f) && tuning(TUNE_TC_WIDE) != TUNE_UNSET)
+    pl.tc_wide = tuning(TUNE_TC_WIDE) != 0;                                       // tests: hoisted kernels on a shape the fused kernel covers
   if (pl.tc_wide) pl.wx = cv.take<float>(tc_wide_workspace_floats(dims_of(p)));
   if (p.weight_layout == FGRNN_LAYOUT_HI && (pl.path == FGRNN_PATH_GENERIC || pl.path == FGRNN_PATH_LOWRANK)) {
     if (p.rW == 0) pl.Wc = cv.take<float>((size_t)p.I * p.H);
@@ -308,6 +326,17 @@ using namespace fgrnn;
 extern "C" {
 
 int fgrnn_abi_version(void) { return FGRNN_ABI_VERSION; }
+
+int fgrnn_debug_set_tuning(const char* name, const char* value) {
+  if (!name) return FGRNN_ERR_NULL;
+  tune_init();
+  for (int k = 0; k < TUNE_COUNT; ++k)
+    if (!strcmp(name, kTuneNames[k])) {
+      g_tune[k].store(value && value[0] ? tune_parse(k, value) : TUNE_UNSET);
+      return FGRNN_OK;
+    }
+  return fail(FGRNN_ERR_ENUM, "unknown tuning key %s", name);
+}
 uint64_t fgrnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* fgrnn_last_error_detail(void) { return g_detail; }
 

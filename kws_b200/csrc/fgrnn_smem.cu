@@ -361,8 +361,8 @@ static int cfg_rows(char c) { return c == 'A' ? CfgA::BM : c == '7' ? CfgA7::BM 
 
 // tile configuration: 'A' 64 rows, '7' 56 rows, 'B' 32 rows x 2 CTAs/SM, 'C' 16 rows x 2 CTAs/SM
 static char pick_cfg(const Dims& d, bool backward) {
-  if (const char* env = getenv("FGRNN_SMEM_CFG")) {            // tuning / test override
-    const char c = env[0] == 'A' && env[1] == '7' ? '7' : env[0];
+  if (tuning(TUNE_SMEM_CFG) != TUNE_UNSET) {                    // tuning / test override
+    const char c = (char)tuning(TUNE_SMEM_CFG);
     const bool two_ok = fwd_smem_bytes(d.I, 32) * 2 + 2048 <= 227 * 1024 || backward;
     if (c == 'A' || c == '7') return c;
     if ((c == 'B' || c == 'C') && two_ok) return c;
@@ -400,7 +400,7 @@ static int launch_fwd_t(const SmemFwdArgs& a, cudaStream_t stream) {
 int launch_smem_fwd(const SmemFwdArgs& a_, cudaStream_t stream) {
   SmemFwdArgs a = a_;
   a.fast_nl = 3;
-  if (const char* env = getenv("FGRNN_FAST_NL")) a.fast_nl = atoi(env) & 3;   // bit0 sigmoid, bit1 tanh
+  if (tuning(TUNE_FAST_NL) != TUNE_UNSET) a.fast_nl = tuning(TUNE_FAST_NL) & 3;   // bit0 sigmoid, bit1 tanh
   switch (pick_cfg(a.d, false)) {
     case 'A': return launch_fwd_t<CfgA>(a, stream);
     case '7': return launch_fwd_t<CfgA7>(a, stream);

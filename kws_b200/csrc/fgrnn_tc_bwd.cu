@@ -593,7 +593,7 @@ bool tc_bwd_rec_supports(const Dims& d) {
 // 16-row sub-tiles while the batch fits one wave of 32-row CTAs; FGRNN_TC_BR_NS=16|32 overrides (tests, benchmarks)
 static int br_ns_for(int B) {
   int ns = B <= 148 * 32 ? 16 : 32;
-  if (const char* e = getenv("FGRNN_TC_BR_NS")) { if (atoi(e) == 16) ns = 16; else if (atoi(e) == 32) ns = 32; }
+  if (tuning(TUNE_TC_BR_NS) == 16) ns = 16; else if (tuning(TUNE_TC_BR_NS) == 32) ns = 32;
   return ns;
 }
 int tc_bwd_rec_ctas(const Dims& d) { const int rows = br_ns_for(d.B) * BR_NT; return (d.B + rows - 1) / rows; }

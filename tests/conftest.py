@@ -54,3 +54,17 @@ def params_from_golden(g, prefix="p_"):
 def lib():
     from kws_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture
+def tuning():
+    """Set launcher tuning keys for one test (kws_b200._lib.set_tuning) and clear them afterwards."""
+    from kws_b200 import _lib
+    used = []
+
+    def set_(name, value):
+        _lib.set_tuning(name, value)
+        used.append(name)
+    yield set_
+    for name in used:
+        _lib.set_tuning(name, None)

@@ -45,9 +45,9 @@ def test_ingest_applies_the_loader_normalisation_bit_for_bit():
 def test_permuted_view_runs_without_a_torch_copy_and_matches_contiguous_input():
     from kws_b200 import _lib, engine
     torch.manual_seed(4)
-    p = O.init_params(64, 128)
+    p = O.init_params(32, 128)
     params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
-    x_bft = torch.randn(96, 64, 99, device=dev())
+    x_bft = torch.randn(96, 32, 99, device=dev())
     view = x_bft.permute(2, 0, 1)
     n0 = _lib.launch_count()
     out_v = engine.forward(view, params, None, layout="IH", batch_first=False)[0]

@@ -307,11 +307,11 @@ def test_empty_batch_and_sequence():
 @pytest.mark.parametrize("path", ["generic", "smem"])
 @pytest.mark.parametrize("layout", ["IH", "HI"])
 @pytest.mark.parametrize("cfg", ["A", "A7", "B", "C"])
-def test_kernel_families_agree_with_oracle(path, layout, cfg, monkeypatch):
+def test_kernel_families_agree_with_oracle(path, layout, cfg, tuning):
     """Every kernel family that covers the flagship shape (I=32, H=128, full rank) is checked on
     its own, in both weight layouts, forward and backward, with a ragged batch."""
     from kws_b200 import _lib, engine
-    monkeypatch.setenv("FGRNN_SMEM_CFG", cfg)
+    tuning("FGRNN_SMEM_CFG", cfg)
     if path == "generic" and cfg != "A":
         pytest.skip("tile override only affects the shared-memory family")
     torch.manual_seed(77)

@@ -54,11 +54,11 @@ def test_tcgen05_forward_vs_oracle(B, T, I, layout, h0):
 
 
 @pytest.mark.parametrize("ns,nt", [("16", "2"), ("16", "4"), ("32", "2")])
-def test_tcgen05_forward_every_tile_configuration(monkeypatch, ns, nt):
+def test_tcgen05_forward_every_tile_configuration(tuning, ns, nt):
     """The launcher picks 2x16-row sub-tiles for one-wave batches and 4x16 beyond; FGRNN_TC_NS / FGRNN_TC_NT pin a
     configuration.  All three (incl. the 2x32 variant) must meet the tolerance on ragged, multi-CTA, saved-gate runs."""
-    monkeypatch.setenv("FGRNN_TC_NS", ns)
-    monkeypatch.setenv("FGRNN_TC_NT", nt)
+    tuning("FGRNN_TC_NS", ns)
+    tuning("FGRNN_TC_NT", nt)
     for (B, T, I, layout, h0, save) in [(77, 9, 32, "HI", True, False), (300, 17, 16, "IH", False, True), (33, 4, 24, "IH", True, False)]:
         out, last, ref, z_s, c_s = _run(B, T, I, layout, h0, seed=21 + B, save=save)
         assert state_ratio(out, ref) <= 1.0, (ns, nt, B)
@@ -138,10 +138,10 @@ def test_tcgen05_backward_against_autograd(B, T, I, layout, h0_given, bf):
 
 
 @pytest.mark.parametrize("ns", ["16", "32"])
-def test_tcgen05_backward_both_sub_tile_widths(monkeypatch, ns):
+def test_tcgen05_backward_both_sub_tile_widths(tuning, ns):
     """The reverse recurrence takes 16-row sub-tiles while the batch fits one wave of 32-row CTAs and 32-row ones
     beyond; FGRNN_TC_BR_NS pins the width (the per-CTA partial rows follow it)."""
-    monkeypatch.setenv("FGRNN_TC_BR_NS", ns)
+    tuning("FGRNN_TC_BR_NS", ns)
     test_tcgen05_backward_against_autograd(77, 9, 32, "HI", True, True)
     test_tcgen05_backward_against_autograd(130, 7, 16, "IH", False, False)
 

@@ -73,9 +73,9 @@ def test_wide_forward_vs_oracle(I, H, B, T, bf, gate, layout):
     assert float((rebuilt - hs).abs().max()) < 2e-6
 
 
-def test_wide_kernels_on_the_flagship_shape_match_golden(monkeypatch):
+def test_wide_kernels_on_the_flagship_shape_match_golden(tuning):
     """H = 128, I = 32 through the hoisted kernels (the fused kernel's shape) against the reference-minted golden."""
-    monkeypatch.setenv("FGRNN_TC_WIDE", "1")
+    tuning("FGRNN_TC_WIDE", "1")
     g = load_golden("c1_bf")
     from conftest import params_from_golden
     p = params_from_golden(g)
