@@ -384,30 +384,48 @@ class Bench:
         graphed, cap = False, None
 
         if train:
-            from kws_b200 import graphs, rnn as krnn
+            from kws_b200 import graphs, rnn as krnn, train_step
             torch.manual_seed(0)
             layer = krnn.FastGRNN(I, H, wRank=w["wR"], uRank=w["uR"], batch_first=False).to(dev)
             head = torch.nn.Linear(H, 13).to(dev)
             plist = list(layer.cell.parameters()) + list(head.parameters())
             if world > 1:
                 sharding.broadcast_parameters(plist)
-            bucket = sharding.GradBucket(plist)
-            opt = torch.optim.SGD(plist, lr=1e-3)
             x_tm = x.transpose(0, 1).contiguous()
             labels = torch.randint(0, 13, (B,), device=dev)
+            fused = args.train_api == "fused"
+            if fused:
+                # kws_b200.train_step: recurrence, fused head+loss kernel, BPTT from the last state's gradient, flat SGD
+                stepper = train_step.LastStateTrainStep(layer, head, 1e-3, data_parallel=False)
+                stepper.world = world
 
-            def step_compute():                       # forward, loss head, BPTT: gradients land in the flat bucket
-                bucket.zero()
-                hs = layer(x_tm)
-                logp = torch.nn.functional.log_softmax(head(hs[-1]), dim=1)      # model.py:228-230
-                loss = torch.nn.functional.nll_loss(logp, labels)
-                loss.backward()
+                def step_compute():
+                    stepper.compute(x_tm, labels)
 
-            def step():
-                step_compute()
-                if world > 1:
-                    bucket.all_reduce_mean(group=self.cap_group)
-                opt.step()
+                def step():
+                    step_compute()
+                    if world > 1:
+                        self.dist.all_reduce(stepper.flat_grads, group=self.cap_group)     # SUM; 1/world folded into the SGD kernel
+                    train_step.sgd_flat(stepper.flat_params, stepper.flat_grads, stepper.lr, 1.0 / world)
+                opt_step = lambda: train_step.sgd_flat(stepper.flat_params, stepper.flat_grads, stepper.lr, 1.0 / world)   # noqa: E731
+            else:
+                # the module API through autograd, as the unchanged trainClassifier.py drives it
+                bucket = sharding.GradBucket(plist)
+                opt = torch.optim.SGD(plist, lr=1e-3)
+                opt_step = opt.step
+
+                def step_compute():                   # forward, loss head, BPTT: gradients land in the flat bucket
+                    bucket.zero()
+                    hs = layer(x_tm)
+                    logp = torch.nn.functional.log_softmax(head(hs[-1]), dim=1)      # model.py:228-230
+                    loss = torch.nn.functional.nll_loss(logp, labels)
+                    loss.backward()
+
+                def step():
+                    step_compute()
+                    if world > 1:
+                        bucket.all_reduce_mean(group=self.cap_group)
+                    opt.step()
 
             run_step = step
             if not args.no_graph:
@@ -426,12 +444,15 @@ class Bench:
                         run_step, graphed = cap, True
                     else:
                         cap = graphs.CapturedStep(step_compute, warmup=1)
-                        cap_opt = graphs.CapturedStep(opt.step, warmup=1)
+                        cap_opt = graphs.CapturedStep(opt_step, warmup=1)
                         cap.launches += cap_opt.launches
 
                         def run_step():
                             cap()
-                            bucket.all_reduce_mean(group=self.cap_group)
+                            if fused:
+                                self.dist.all_reduce(stepper.flat_grads, group=self.cap_group)
+                            else:
+                                bucket.all_reduce_mean(group=self.cap_group)
                             cap_opt()
                         graphed = True
                 except Exception as e:                # noqa: BLE001 -- report and time the eager step instead
@@ -492,7 +513,9 @@ class Bench:
         if os.path.isfile(prof):
             with open(prof) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        kernel = ("forward recurrence + loss head + BPTT (reverse recurrence, contractions, reduce) + SGD, one CUDA graph"
+        kernel = (("forward recurrence + fused head/loss kernel + BPTT from the last state's gradient (reverse recurrence, "
+                   "contraction, reduce) + flat SGD, one CUDA graph" if args.train_api == "fused" else
+                   "module API through autograd: forward recurrence + loss head + BPTT + SGD, one CUDA graph")
                   if train else "fgrnn forward (%s path)" % plan)
         roof = {"bound": "hbm", "achieved": achieved, "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak,
                 "traffic": traffic, "kernel": kernel, "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms,
@@ -572,6 +595,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other configurations")
     ap.add_argument("--no-graph", action="store_true", help="training workloads: time the eager step, not the CUDA graph")
+    ap.add_argument("--train-api", default="fused", choices=["fused", "module"],
+                    help="training workloads: kws_b200.train_step (default) or the module API through autograd")
     ap.add_argument("--chunk-rows", type=int, default=1024, help="rows per pipeline chunk of the host-buffer API")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FGRNN_ABI_VERSION 2
+#define FGRNN_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FGRNN_API __attribute__((visibility("default")))
@@ -141,6 +141,12 @@ typedef struct FgrnnBackward {
   float* d_zeta; float* d_nu;                              /* [1,1] */
   float* d_h0;                                             /* [B,H] */
   void* workspace; size_t workspace_bytes;
+  /* ABI 3.  First time step that has an upstream gradient: grad_h holds T - grad_t0 steps, entry (b, t - grad_t0) is
+     dL/dh_t for t >= grad_t0, and dL/dh_t = 0 before.  0 = a gradient for every step (the reference's contract);
+     T - 1 = only the LAST state is consumed (model.py:227-231: hidden2keyword(out[-1])), grad_h is then one [B,H]
+     matrix and the dense, all-zero [T,B,H] gradient autograd would build for out[-1] is never written nor read. */
+  int32_t grad_t0;
+  int32_t reserved1;
 } FgrnnBackward;
 
 /* Bytes of device workspace the call needs (0 is possible). 256-byte aligned base required. */
@@ -177,6 +183,23 @@ FGRNN_API uint64_t fgrnn_launch_count(void);
    preprocessing.py:60-76 applied on the way, with the reference's two correctly rounded operations. */
 FGRNN_API int fgrnn_ingest_bft(const float* src, int64_t stride_b, int64_t stride_f, int64_t stride_t, float* dst,
                                const float* mean, const float* stdev, int32_t B, int32_t F, int32_t T, int32_t device, void* stream);
+
+/* Classifier head of the keyword spotter on the LAST hidden state, forward + loss + backward in one launch
+   (model.py:227-231 hidden2keyword + log_softmax, NLLLoss of trainClassifier.py:236; the torch version is ~15 launches):
+     logits = h . W^T + b; loss = -mean_b log_softmax(logits)[b, labels[b]];
+     dW [C,H], db [C], dh [B,H] (optional) = gradients of the MEAN loss; logp [B,C] optional.
+   h / dh are given by row stride (e.g. the last time step of the hidden states / of a zeroed grad_h buffer).
+   workspace: fgrnn_head_workspace_bytes(B,H,C) bytes, its first 4 bytes ZERO on entry (the kernel leaves them zero).
+   C <= 16, H % 4 == 0.  Per-CTA partial sums are added in a fixed order: results are run-to-run identical. */
+FGRNN_API size_t fgrnn_head_workspace_bytes(int32_t B, int32_t H, int32_t C);
+FGRNN_API int fgrnn_head_nll(const float* h, int64_t h_stride, const float* W, const float* b, const int64_t* labels,
+                             float* loss, float* dW, float* db, float* dh, int64_t dh_stride, float* logp,
+                             void* workspace, size_t workspace_bytes, int32_t B, int32_t H, int32_t C, int32_t device, void* stream);
+
+/* Plain SGD step over one flat parameter buffer and one flat gradient bucket (torch.optim.SGD without momentum /
+   weight decay, trainClassifier.py:240): params[i] -= lr * (grad_scale * grads[i]); grad_scale = 1 / world size when the
+   bucket holds the all-reduced SUM of the ranks' gradients. */
+FGRNN_API int fgrnn_sgd_flat(float* params, const float* grads, int64_t n, float lr, float grad_scale, int32_t device, void* stream);
 
 /* Tuning / test override of the launchers' tile configuration.  Keys are the names of the environment variables that set
    the same values at process start (FGRNN_TC_NS, FGRNN_TC_NT, FGRNN_TC_BR_NS, FGRNN_TC_WIDE, FGRNN_FAST_NL,

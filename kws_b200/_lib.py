@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums (include/fastgrnn_b200.h)
 OK, ERR_NULL, ERR_SHAPE, ERR_ENUM, ERR_ALIGN, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE, ERR_VERSION = range(9)
@@ -66,6 +66,7 @@ class FgrnnBackward(C.Structure):
         ("d_bias_gate", _fp), ("d_bias_update", _fp), ("d_zeta", _fp), ("d_nu", _fp),
         ("d_h0", _fp),
         ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+        ("grad_t0", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -82,6 +83,11 @@ SYMBOLS = {
     "fgrnn_last_error_detail": (C.c_char_p, []),
     "fgrnn_abi_version": (C.c_int, []),
     "fgrnn_launch_count": (C.c_uint64, []),
+    "fgrnn_head_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "fgrnn_head_nll": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p]),
+    "fgrnn_sgd_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "fgrnn_debug_poison_onchip": (C.c_int, [C.c_int, C.c_void_p]),
     "fgrnn_debug_set_tuning": (C.c_int, [C.c_char_p, C.c_char_p]),
     "fgrnn_ingest_bft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -240,7 +240,7 @@ bool tc_bwd_ok(const FgrnnBackward& g) {
   // requirements as the forward's x map (positive strides, 16-byte multiples) -- an expanded gradient with a
   // zero stride (e.g. from out.sum((0,1)).backward()) falls through to the FFMA families instead of failing
   // in cuTensorMapEncodeTiled after the path has been chosen
-  if (!tc_x_tma_ok(g.grad_h, g.grad_stride_b, g.grad_stride_t, FGRNN_F32, p.B, p.T)) return false;
+  if (!tc_x_tma_ok(g.grad_h, g.grad_stride_b, g.grad_stride_t, FGRNN_F32, p.B, p.T - g.grad_t0)) return false;
   if (g.hs && !tc_x_tma_ok(g.hs, g.hs_stride_b, g.hs_stride_t, FGRNN_F32, p.B, p.T)) return false;
   if (!fits_u32_bytes((int64_t)p.B * p.H)) return false;
   return aligned16(p.U) && aligned16(p.h0) && aligned16(g.grad_h) && mult4(g.grad_stride_b) && mult4(g.grad_stride_t) &&
@@ -293,6 +293,7 @@ int validate_backward(const FgrnnBackward& g) {
   if (has_scales(g.p)) return fail(FGRNN_ERR_SHAPE, "gate_scale / update_scale (folded eval-mode BatchNorm) are forward only");
   if ((int64_t)g.p.B * g.p.T > 0) {
     if (!g.grad_h) return fail(FGRNN_ERR_NULL, "grad_h must be a CUDA tensor (NULL)");
+    if (g.grad_t0 < 0 || g.grad_t0 >= g.p.T) return fail(FGRNN_ERR_SHAPE, "grad_t0 = %d must be in [0, T = %d)", g.grad_t0, g.p.T);
     if (!g.hs && g.p.T > 1) return fail(FGRNN_ERR_NULL, "hidden_states must be a CUDA tensor (NULL)");
     if (!g.z_s || !g.c_s) return fail(FGRNN_ERR_NULL, "z / h_prime must be CUDA tensors (NULL)");
   }
@@ -525,7 +526,7 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   if (pl.path == FGRNN_PATH_SMEM || pl.path == FGRNN_PATH_TCGEN05) {
     SmemBwdArgs s{};
     s.d = dims_of(p); s.layout = p.weight_layout; s.U = p.U; s.zeta = p.zeta; s.nu = p.nu;
-    s.grad_h = g->grad_h; s.gsb = g->grad_stride_b; s.gst = g->grad_stride_t;
+    s.grad_h = g->grad_h; s.gsb = g->grad_stride_b; s.gst = g->grad_stride_t; s.gt0 = g->grad_t0;
     s.hs = g->hs; s.hsb = g->hs_stride_b; s.hst = g->hs_stride_t;
     s.h0 = p.h0; s.z_s = g->z_s; s.c_s = g->c_s;
     s.dpre_ws = pl.dpre; s.rec_partial = pl.rec_partial; s.d_h0 = g->d_h0;
@@ -535,7 +536,7 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   r.d = dims_of(p);
   r.zeta = p.zeta; r.nu = p.nu;
   r.UT = UT; r.U2T = U2T; r.U1T = U1T;
-  r.grad_h = g->grad_h; r.gsb = g->grad_stride_b; r.gst = g->grad_stride_t;
+  r.grad_h = g->grad_h; r.gsb = g->grad_stride_b; r.gst = g->grad_stride_t; r.gt0 = g->grad_t0;
   r.hs = g->hs; r.hsb = g->hs_stride_b; r.hst = g->hs_stride_t;
   r.h0 = p.h0; r.z_s = g->z_s; r.c_s = g->c_s;
   r.dpre_ws = pl.dpre; r.rec_partial = pl.rec_partial; r.d_h0 = g->d_h0;

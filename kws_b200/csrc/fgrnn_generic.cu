@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(GEN_NT) gen_bwd_rec_kernel(const BwdRecArgs a)
         if (r < nrows) {
           const size_t row = (size_t)(row0 + r);
           const size_t sidx = ((size_t)t * d.B + row) * d.H + n;
-          const float G = a.grad_h[row * a.gsb + (size_t)t * a.gst + n] + dc_s[r * Hp + n];   // cu:474
+          const float G = (t >= a.gt0 ? a.grad_h[row * a.gsb + (size_t)(t - a.gt0) * a.gst + n] : 0.0f) + dc_s[r * Hp + n];   // cu:474
           const float z = a.z_s[sidx], c = a.c_s[sidx];
           float hp;
           if (t > 0) hp = a.hs[row * a.hsb + (size_t)(t - 1) * a.hst + n];

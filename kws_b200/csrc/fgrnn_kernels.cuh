@@ -29,7 +29,7 @@ struct BwdRecArgs {
   const float *zeta, *nu;
   // transposed canonical recurrent weights: UT[n][k] = Uc[k][n];  U2T[H][rU];  U1T[rU][H]
   const float *UT, *U2T, *U1T;
-  const float* grad_h; int64_t gsb, gst;
+  const float* grad_h; int64_t gsb, gst; int gt0;      // grad_h[b][t - gt0] for t >= gt0, zero upstream gradient before
   const float* hs; int64_t hsb, hst;
   const float* h0;
   const float *z_s, *c_s;
@@ -101,7 +101,7 @@ struct SmemBwdArgs {
   int layout;
   const float* U;
   const float *zeta, *nu;
-  const float* grad_h; int64_t gsb, gst;
+  const float* grad_h; int64_t gsb, gst; int gt0;      // grad_h[b][t - gt0] for t >= gt0, zero upstream gradient before
   const float* hs; int64_t hsb, hst;
   const float* h0;
   const float *z_s, *c_s;

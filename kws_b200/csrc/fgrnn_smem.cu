@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) smem_bwd_rec_kernel(const 
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
         if (row < d.B) {
           const size_t sidx = ((size_t)t * d.B + row) * H + c;
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.grad_h + (size_t)row * a.gsb + (size_t)t * a.gst + c));
+          const float4 g4 = t >= a.gt0 ? __ldg(reinterpret_cast<const float4*>(a.grad_h + (size_t)row * a.gsb + (size_t)(t - a.gt0) * a.gst + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.z_s + sidx));
           const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.c_s + sidx));
           float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);

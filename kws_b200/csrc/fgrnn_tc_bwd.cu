@@ -415,8 +415,9 @@ static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& m
           const uint32_t fb = bar(B_SFULL + q % BR_NB), ring = smem_u32(sm + L.stage);
           const int u0 = (4 * q) % BR_RU;
           auto unit = [&](int k) { return ring + (uint32_t)(((u0 + k) % BR_RU) * BR_ARR); };
-          mbar_expect_tx(fb, (uint32_t)BR_ARR * (with_hp ? 4u : 3u));
-          if (g_time_outer) tma_load_3d(unit(0), &maps.g, 0, first, t, fb); else tma_load_3d(unit(0), &maps.g, 0, t, first, fb);
+          const bool with_g = t >= a.gt0;               // no upstream gradient before gt0: the tile is not fetched
+          mbar_expect_tx(fb, (uint32_t)BR_ARR * ((with_hp ? 3u : 2u) + (with_g ? 1u : 0u)));
+          if (with_g) { if (g_time_outer) tma_load_3d(unit(0), &maps.g, 0, first, t - a.gt0, fb); else tma_load_3d(unit(0), &maps.g, 0, t - a.gt0, first, fb); }
           tma_load_3d(unit(1), &maps.z, 0, first, t, fb);
           tma_load_3d(unit(2), &maps.c, 0, first, t, fb);
           if (t > 0) {
@@ -510,13 +511,13 @@ static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& m
       const float* tz = ring + ((u0 + 1) % BR_RU) * (BR_ARR / 4);
       const float* tcc = ring + ((u0 + 2) % BR_RU) * (BR_ARR / 4);
       const float* th = ring + ((u0 + 3) % BR_RU) * (BR_ARR / 4);
-      const bool hp_zero = t == 0 && hp_zero_at_t0;
+      const bool hp_zero = t == 0 && hp_zero_at_t0, g_zero = t < a.gt0;
       uint32_t hi[PAIRS], mid[PAIRS], lo[PAIRS];
       float2 dp[PAIRS];
 #pragma unroll
       for (int q = 0; q < PAIRS; ++q) {
         const int e = (2 * q) * BR_H;
-        const float2 g = make_float2(tg[e], tg[e + BR_H]);
+        const float2 g = g_zero ? make_float2(0.f, 0.f) : make_float2(tg[e], tg[e + BR_H]);
         const float2 z = make_float2(tz[e], tz[e + BR_H]);
         const float2 c = make_float2(tcc[e], tcc[e + BR_H]);
         const float2 hp = hp_zero ? make_float2(0.f, 0.f) : make_float2(th[e], th[e + BR_H]);
@@ -604,7 +605,7 @@ static int launch_tc_bwd_rec_ns(const SmemBwdArgs& a, cudaStream_t stream) {
   const Dims& d = a.d;
   BrMaps maps;
   int g_to = 0, hs_to = 0, dummy = 0, rc;
-  if ((rc = make_row_tile_map(&maps.g, a.grad_h, false, BR_H, d.B, d.T, a.gsb, a.gst, BR_NS, &g_to))) return rc;
+  if ((rc = make_row_tile_map(&maps.g, a.grad_h, false, BR_H, d.B, d.T - a.gt0, a.gsb, a.gst, BR_NS, &g_to))) return rc;
   if ((rc = make_row_tile_map(&maps.z, a.z_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
   if ((rc = make_row_tile_map(&maps.c, a.c_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
   // T == 1 never reads the hidden states (h_{t-1} is h0): any valid pointer keeps the descriptor well formed

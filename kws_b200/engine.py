@@ -271,11 +271,15 @@ def backward(grad_h: torch.Tensor, x: torch.Tensor, hs: torch.Tensor, z_s: torch
              params: Dict[str, torch.Tensor], h0: Optional[torch.Tensor] = None, *,
              layout: str = "HI", batch_first: bool = False, gate_nl="sigmoid", update_nl="tanh",
              need_dx: bool = True, need_dh0: bool = True, need_params: bool = True,
-             grad_bucket: Optional[torch.Tensor] = None, force_path: int = -1) -> Dict[str, torch.Tensor]:
+             grad_bucket: Optional[torch.Tensor] = None, force_path: int = -1,
+             grad_t0: int = 0) -> Dict[str, torch.Tensor]:
     """Backward-through-time.  Returns a dict with ``x``, ``h0`` and one entry per
     parameter (same layout/shape as the parameter).  When ``grad_bucket`` (a flat
     fp32 tensor of ``grad_bucket_numel`` floats) is given, the parameter gradients
-    are written straight into it (views returned) so one all-reduce covers them."""
+    are written straight into it (views returned) so one all-reduce covers them.
+    ``grad_t0``: ``grad_h`` holds the steps t >= grad_t0 only (T - grad_t0 of them) and the
+    earlier steps have no upstream gradient; ``grad_t0 = T - 1`` is the keyword spotter's case
+    (model.py:227-231 consumes ``out[-1]``), ``grad_h`` then being one [1,B,H] / [B,1,H] slab."""
     lib = _lib.load()
     pr = _Problem(x, params, h0, layout, batch_first, gate_nl, update_nl, force_path)
     dev, B, T, H, I = pr.device, pr.B, pr.T, pr.H, pr.I
@@ -288,8 +292,12 @@ def backward(grad_h: torch.Tensor, x: torch.Tensor, hs: torch.Tensor, z_s: torch
     if hs.stride(2) != 1 and H > 1:
         hs = hs.contiguous()
     exp = (B, T, H) if pr.batch_first else (T, B, H)
-    if tuple(grad_h.shape) != exp or tuple(hs.shape) != exp:
-        raise RuntimeError("grad_h/hidden_states must have shape %s" % (exp,))
+    grad_t0 = int(grad_t0)
+    if T > 0 and not (0 <= grad_t0 < T):
+        raise RuntimeError("grad_t0 = %d must be in [0, T = %d)" % (grad_t0, T))
+    gexp = (B, T - grad_t0, H) if pr.batch_first else (T - grad_t0, B, H)
+    if tuple(grad_h.shape) != gexp or tuple(hs.shape) != exp:
+        raise RuntimeError("grad_h must have shape %s and hidden_states %s" % (gexp, exp))
     for name, t in (("z", z_s), ("h_prime", c_s)):
         if not t.is_cuda:
             raise RuntimeError("%s must be a CUDA tensor" % name)
@@ -300,6 +308,9 @@ def backward(grad_h: torch.Tensor, x: torch.Tensor, hs: torch.Tensor, z_s: torch
         pr.fill(g.p)
         g.grad_h = grad_h.data_ptr() if grad_h.numel() else None
         g.grad_stride_b, g.grad_stride_t = pr.strides(grad_h)
+        g.grad_t0 = grad_t0
+        if T - grad_t0 == 1:                 # a single step: its stride is never used, keep it well formed for the TMA map
+            g.grad_stride_t = max(int(g.grad_stride_t), B * H)
         g.hs = hs.data_ptr() if hs.numel() else None
         g.hs_stride_b, g.hs_stride_t = pr.strides(hs)
         g.z_s = z_s.data_ptr() if z_s.numel() else None
