@@ -22,7 +22,7 @@ void set_error_detail(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG"};
+static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::once_flag g_tune_once;
 static int tune_parse(int key, const char* e) {
@@ -156,6 +156,15 @@ bool lr_fwd_ok(const FgrnnForward& f) {
          aligned16(p.U2) && aligned16(p.bias_gate) && aligned16(p.bias_update) && aligned16(p.h0) && aligned16(f.out) &&
          mult4(f.out_stride_b) && mult4(f.out_stride_t) && aligned16(f.h_last) && aligned16(f.save_z) &&
          aligned16(f.save_c) && (!f.save_z == !f.save_c);
+}
+
+// low-rank family on the tensor cores (fgrnn_tc_lr.cu): x by TMA, inference forward only; FGRNN_TC_LR=0 keeps the FFMA kernel
+bool tc_lr_ok(const FgrnnForward& f) {
+  const FgrnnProblem& p = f.p;
+  if (tuning(TUNE_TC_LR) == 0) return false;
+  return lr_fwd_ok(f) && tc_lr_supports(dims_of(p)) && !f.save_z && !f.save_c &&
+         tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T) &&
+         fits_u32_bytes(f.out_stride_b) && fits_u32_bytes(f.out_stride_t) && fits_u32_bytes((int64_t)p.B * p.H);
 }
 
 int select_fwd_path(const FgrnnForward& f) {
@@ -448,7 +457,8 @@ int fgrnn_forward(const FgrnnForward* f, void* stream_) {
     if (rc) return rc;
     a.Wc = pl.Wc; a.Uc = pl.Uc; a.W1c = pl.W1c; a.W2c = pl.W2c; a.U1c = pl.U1c; a.U2c = pl.U2c;
   }
-  return pl.path == FGRNN_PATH_LOWRANK ? launch_lr_fwd(a, stream) : launch_gen_fwd(a, stream);
+  if (pl.path == FGRNN_PATH_LOWRANK) return tc_lr_ok(*f) ? launch_tc_lr_fwd(a, stream) : launch_lr_fwd(a, stream);
+  return launch_gen_fwd(a, stream);
 }
 
 int fgrnn_backward(const FgrnnBackward* g, void* stream_) {

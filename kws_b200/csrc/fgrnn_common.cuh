@@ -22,7 +22,7 @@ void count_launch(int n = 1);
 
 // Tuning / test overrides of the launchers.  Each key takes its default from the environment variable of the same name,
 // read ONCE per process (no getenv on the launch path); fgrnn_debug_set_tuning changes it afterwards (tests).
-enum TuneKey { TUNE_TC_NS = 0, TUNE_TC_NT, TUNE_TC_BR_NS, TUNE_TC_WIDE, TUNE_FAST_NL, TUNE_SMEM_CFG, TUNE_COUNT };
+enum TuneKey { TUNE_TC_NS = 0, TUNE_TC_NT, TUNE_TC_BR_NS, TUNE_TC_WIDE, TUNE_FAST_NL, TUNE_SMEM_CFG, TUNE_TC_LR, TUNE_COUNT };
 constexpr int TUNE_UNSET = -2147483647 - 1;
 int tuning(TuneKey key);          // TUNE_UNSET when neither the environment nor a test set it
 
@@ -76,6 +76,9 @@ __device__ __forceinline__ float sigmoid_f(float a) { return 1.0f / (1.0f + expf
 // asserted by the GPU parity tests.
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// clamps that keep NaN (fmaxf / fminf return the other operand): a NaN pre-activation must stay NaN, as in the reference
+__device__ __forceinline__ float fmax_nan(float a, float b) { float y; asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float y; asm("min.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float a) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * a)); }
 __device__ __forceinline__ float tanh_fast(float b) {
   const float e = ex2_approx(2.8853900817779268f * b);

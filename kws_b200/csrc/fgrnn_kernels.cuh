@@ -22,6 +22,9 @@ int launch_gen_fwd(const FwdArgs& a, cudaStream_t stream);
 // low-rank persistent FFMA forward (fgrnn_lr.cu): H = 256, W1/W2/U1/U2 resident in shared memory
 bool lr_path_supports(const Dims& d);
 int launch_lr_fwd(const FwdArgs& a, cudaStream_t stream);
+// low-rank recurrence on the tensor cores (fgrnn_tc_lr.cu): H = 256, uRank <= 32, wRank <= 16, I <= 32; two chained tcgen05 stages
+bool tc_lr_supports(const Dims& d);
+int launch_tc_lr_fwd(const FwdArgs& a, cudaStream_t stream);
 
 // ---- backward, serial part ---------------------------------------------------------------
 struct BwdRecArgs {

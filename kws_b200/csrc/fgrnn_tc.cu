@@ -168,11 +168,11 @@ static __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, cons
   float2 ag, eg, eu;
   if (ONE_EX2) {
     // one clamp on tot keeps e_g <= 2^30; e_u = e_g^2 * ratio follows the clamped value consistently (tanh is -1 there)
-    tot.x = fmaxf(tot.x, k.tmin); tot.y = fmaxf(tot.y, k.tmin);
+    tot.x = fmax_nan(tot.x, k.tmin); tot.y = fmax_nan(tot.y, k.tmin);
     ag = __ffma2_rn(tot, k.kS, k.cg);                          // -(pre + b_g) * log2(e)
   } else {
     ag = __ffma2_rn(tot, k.kS, k.cg);
-    ag.x = fminf(ag.x, 60.0f); ag.y = fminf(ag.y, 60.0f);      // the two exponents are clamped separately
+    ag.x = fmin_nan(ag.x, 60.0f); ag.y = fmin_nan(ag.y, 60.0f);      // the two exponents are clamped separately
   }
 #ifdef TC_EXP_NO_MUFU
   eg = __fmul2_rn(ag, ag);
@@ -183,7 +183,7 @@ static __device__ __forceinline__ float2 gate_update2(float2 tot, float2 h, cons
     eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                 // cu = exp(2 (b_g - b_u))
   } else {
     float2 au = __ffma2_rn(tot, k.k2S, k.cu2);                 // -2 (pre + b_u) * log2(e)
-    au.x = fminf(au.x, 60.0f); au.y = fminf(au.y, 60.0f);
+    au.x = fmin_nan(au.x, 60.0f); au.y = fmin_nan(au.y, 60.0f);
     eu.x = ex2_approx(au.x); eu.y = ex2_approx(au.y);
   }
   const float2 one = make_float2(1.0f, 1.0f);

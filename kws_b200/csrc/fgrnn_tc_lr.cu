@@ -1,0 +1,546 @@
+// tcgen05 / TMEM kernel for the LOW-RANK recurrence (FGRNN_PATH_LOWRANK when the shape fits; BASELINE config 4:
+// H = 256, wRank 16, uRank 32, I = 32):   pre_t = (x_t.W1).W2 + (h_{t-1}.U1).U2   in the reference's factored order
+// (rnn.py:280-287), as two chained tensor-core stages per time step:
+//
+//   stage 1   D1^T[rank][row] = [U1^T ; W1^T] . [h_{t-1} ; x_t]^T     M = 128 (48 used: lanes 0..31 = the U1 ranks,
+//             lanes 32..47 = the W1 ranks; A is block diagonal), K = 256 + KI, N = 32 batch rows
+//   hop       the 48 rank rows leave tensor memory (tcgen05.ld), are un-scaled, split into fp16 hi/lo and written as the
+//             MN-major [48][32] B operand of stage 2 (four of the sub-tile's epilogue warps do this)
+//   stage 2   D2^T[unit][row] = [U2^T | W2^T] . [s ; sx]              two M = 128 tiles (256 units), K = 48, N = 32
+//   epilogue  gate update (rnn.py:289-295) exactly as fgrnn_tc.cu: thread = hidden unit, 32 rows, h in registers
+//
+// Both weight sets stay in TENSOR MEMORY for the whole kernel (fp16 hi/lo pairs): stage 1 takes 288 columns, stage 2
+// 96, which leaves 128 columns = 64 per sub-tile.  D1 and D2 of a sub-tile are never live at the same time (D1 dies when
+// the hop has read it, D2 when the epilogue has read it), so they ALIAS: two sub-tiles of 32 rows per CTA run half a
+// period apart, each with its own pair of MMA-issuing warps.
+//
+// fp32 parity (tools/emulate_tc_lowrank2.py, bit-exact model of the tensor core's accumulate): every accumulator takes
+// its small lo products FIRST and the hi.hi products after them -- the tensor core truncates each addend of an
+// accumulate at 2^-25 of the largest, so a chain that interleaves them (1.3-1.9x the tolerance) loses what the lo-first
+// order keeps (0.49-0.72x); the hi.hi chain of the 16 h k-steps is split over the two accumulators of D1.
+#include <cuda.h>
+
+#include "fgrnn_kernels.cuh"
+#include "fgrnn_tc_common.cuh"
+
+namespace fgrnn {
+
+constexpr int TL_H = 256, TL_NS = 32, TL_NT = 2, TL_ROWS = TL_NS * TL_NT;
+constexpr int TL_RU = 32, TL_RW = 16, TL_K2 = TL_RU + TL_RW;            // padded ranks; K of stage 2
+constexpr int TL_EPI_WARPS = 16, TL_CONV_WARPS = 4, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
+constexpr int TL_THREADS = 32 * (TL_EPI_WARPS + TL_CONV_WARPS + TL_MMA_WARPS);
+constexpr int TL_XBUF = 4, TL_RAW_STAGES = 4, TL_CONV_ROWS = TL_ROWS / TL_CONV_WARPS;
+constexpr int TL_MAX_KI = 32;
+// tensor-memory column map
+constexpr uint32_t TLM_A1_HI = 0, TLM_A1X_HI = 128, TLM_A1_LO = 144, TLM_A1X_LO = 272;     // stage-1 weights: h part | x part
+constexpr uint32_t TLM_A2 = 288;                      // + m * 48 + {0: hi, 24: lo}
+constexpr uint32_t TLM_ACC = 384;                     // + s * 64:  D1 = X | Y (32 columns each), aliased by D2 = tile 0 | tile 1
+constexpr int TL_H_TILE = TL_H * TL_NS * 2;           // one fp16 [256][32] operand tile: 16 KB
+constexpr int TL_S_TILE = TL_K2 * TL_NS * 2;          // one fp16 [48][32] operand tile: 3 KB
+#ifndef TL_STAGGER_NS
+#define TL_STAGGER_NS 900
+#endif
+
+struct TlArgs {
+  FwdArgs f;
+  int KI;               // I rounded up to a multiple of 16 (16 or 32)
+  int x_time_outer;
+};
+struct TlSmem { int h_op, s_op, x_op, raw, bars, misc, total; int x_tile_bytes, raw_stage_bytes; };
+
+__host__ __device__ inline TlSmem tl_smem_layout(int I, int KI, int esz) {
+  TlSmem L;
+  L.x_tile_bytes = TL_NS * KI * 2;
+  L.raw_stage_bytes = TL_CONV_ROWS * I * esz;
+  L.h_op = 0;                                                   // [NT][hi|lo][TL_H_TILE]
+  L.s_op = L.h_op + TL_NT * 2 * TL_H_TILE;                      // [NT][hi|lo][TL_S_TILE]
+  L.x_op = L.s_op + TL_NT * 2 * TL_S_TILE;                      // [XBUF][NT][hi|lo][x_tile_bytes]
+  L.raw = (L.x_op + TL_XBUF * TL_NT * 2 * L.x_tile_bytes + 127) & ~127;
+  L.bars = (L.raw + TL_CONV_WARPS * TL_RAW_STAGES * L.raw_stage_bytes + 15) & ~15;
+  L.misc = L.bars + 48 * 8;
+  L.total = L.misc + 512;
+  return L;
+}
+
+// x tile, K-major [rows][KI]; h and s tiles, MN-major [k][rows] (fgrnn_tc.cu)
+static __device__ __forceinline__ uint64_t tl_desc_kmajor(uint32_t smem_addr, int KI) {
+  const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((KI >> 3) * 128) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+constexpr uint32_t TL_MN_KSTEP = (2 * (TL_NS >> 3) * 128) >> 4;          // descriptor advance per 16 k of an MN-major tile
+constexpr uint32_t TL_X_KSTEP = 256 >> 4;
+constexpr uint32_t TL_IDESC_X = (1u << 4) | ((uint32_t)(TL_NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TL_IDESC_MN = TL_IDESC_X | (1u << 16);
+
+struct TlEpiConst { float2 kS, k2S, cg, cu, cu2, msz, szn; float tmin; };
+
+// rnn.py:289-295 for two rows of one unit on the packed fp32x2 pipe; same arithmetic as TcFwd::gate_update2
+template <bool ONE_EX2>
+static __device__ __forceinline__ float2 tl_gate_update2(float2 tot, float2 h, const TlEpiConst& k) {
+  float2 ag, eg, eu;
+  if (ONE_EX2) { tot.x = fmax_nan(tot.x, k.tmin); tot.y = fmax_nan(tot.y, k.tmin); }
+  ag = __ffma2_rn(tot, k.kS, k.cg);                              // -(pre + b_g) log2(e)
+  if (!ONE_EX2) { ag.x = fmin_nan(ag.x, 60.0f); ag.y = fmin_nan(ag.y, 60.0f); }
+  eg.x = ex2_approx(ag.x); eg.y = ex2_approx(ag.y);
+  if (ONE_EX2) {
+    eu = __fmul2_rn(__fmul2_rn(eg, eg), k.cu);                   // e_u = e_g^2 exp(2 (b_g - b_u))
+  } else {
+    float2 au = __ffma2_rn(tot, k.k2S, k.cu2);
+    au.x = fmin_nan(au.x, 60.0f); au.y = fmin_nan(au.y, 60.0f);
+    eu.x = ex2_approx(au.x); eu.y = ex2_approx(au.y);
+  }
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 a = __fadd2_rn(eg, one), b = __fadd2_rn(eu, one);
+  const float2 ab = __fmul2_rn(a, b);
+  float2 r;
+  r.x = rcp_approx(ab.x); r.y = rcp_approx(ab.y);
+  const float2 z = __fmul2_rn(r, b);                                                          // rnn.py:290
+  const float2 c = __ffma2_rn(__fmul2_rn(r, a), make_float2(2.0f, 2.0f), make_float2(-1.0f, -1.0f));   // rnn.py:292
+  return __ffma2_rn(z, __ffma2_rn(k.msz, c, h), __fmul2_rn(k.szn, c));                        // rnn.py:294-295
+}
+
+struct TlEpiCtx {
+  uint32_t bar_d1full, bar_sready, bar_dfull, bar_hready;
+  uint32_t d1;                        // TMEM address of this warp's 16 columns of D1.X (hop warps)
+  uint32_t d2;                        // TMEM address of this thread's unit in D2 (32 columns)
+  unsigned char* sop;                 // s operand tile address of (k = this lane's rank row, row group 2m), hi part; null = no store
+  unsigned char* hop;                 // h operand tile address of (k = unit, row group 0), hi part
+  float* out; uint32_t out_row, out_step;
+  int rows_left, T;
+  bool hopper;                        // this warp takes part in the hop (lane quadrants 0 and 1)
+  float unscale1;
+};
+
+template <bool HAS_OUT, bool MASKED, bool ONE_EX2>
+static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, const TlEpiConst& kc, float2 (&hst)[TL_NS / 2]) {
+  char* outp = reinterpret_cast<char*>(cx.out);
+  const uint32_t row_bytes = cx.out_row * 4u;
+  for (int t = 0; t < cx.T; ++t) {
+    if (cx.hopper) {
+      // ---- hop: D1 (rank rows) -> fp16 hi/lo B operand of stage 2 -----------------------------------
+      mbar_wait(cx.bar_d1full, t & 1);
+      tc_fence_after();
+      float vx[16], vy[16];
+      tmem_ld16(cx.d1, vx);
+      tmem_ld16(cx.d1 + TL_NS, vy);
+      tmem_ld_wait();
+      if (cx.sop) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            split2(vx[g * 8 + 2 * q] + vy[g * 8 + 2 * q], vx[g * 8 + 2 * q + 1] + vy[g * 8 + 2 * q + 1], cx.unscale1, hi[q], lo[q]);
+          *reinterpret_cast<uint4*>(cx.sop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(cx.sop + TL_S_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_sready);
+    }
+    // ---- D2 -> gate update -> h_t ----------------------------------------------------------------------
+    mbar_wait(cx.bar_dfull, t & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int g = 0; g < TL_NS / 8; ++g) {
+      float v[8];
+      tmem_ld8(cx.d2 + g * 8, v);
+      tmem_ld_wait();
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = g * 4 + q;
+        hst[p] = tl_gate_update2<ONE_EX2>(make_float2(v[2 * q], v[2 * q + 1]), hst[p], kc);
+        const __half2 hh = __float22half2_rn(hst[p]);
+        const float2 hf = __half22float2(hh);
+        const __half2 hl = __float22half2_rn(__fadd2_rn(hst[p], make_float2(-hf.x, -hf.y)));
+        hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&hl);
+      }
+      *reinterpret_cast<uint4*>(cx.hop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(cx.hop + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    fence_proxy_async_smem();                          // st.shared of the h tile -> visible to tcgen05.mma
+    tc_fence_before();                                 // tcgen05.ld of D2 done before stage 1 of the next step overwrites it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready);
+    if (HAS_OUT) {
+#pragma unroll
+      for (int q = 0; q < TL_NS / 2; ++q) {
+        if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
+        if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
+      }
+      outp += (size_t)cx.out_step * 4u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs ta, const __grid_constant__ CUtensorMap xmap) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const FwdArgs& a = ta.f;
+  const Dims d = a.d;
+  const int I = d.I, KI = ta.KI, rU = d.rU, rW = d.rW;
+  const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
+  const TlSmem L = tl_smem_layout(I, KI, esz);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
+  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16]
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int row0 = blockIdx.x * TL_ROWS;
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  // per sub-tile: HREADY (h_{t-1} tile written, D2 drained) | D1FULL | SREADY (s tile written, D1 drained) | DFULL
+  const int B_HREADY = 0, B_D1FULL = 2, B_SREADY = 4, B_DFULL = 6, B_XFULL = 8, B_XEMPTY = 12, B_RAWFULL = 16;
+  constexpr int W_CONV0 = TL_EPI_WARPS, W_MMA = TL_EPI_WARPS + TL_CONV_WARPS;
+
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), 512);
+  if (tid == 0) {
+    for (int s = 0; s < TL_NT; ++s) {
+      mbar_init(bar(B_HREADY + s), TL_EPI_WARPS / TL_NT);
+      mbar_init(bar(B_D1FULL + s), 2);
+      mbar_init(bar(B_SREADY + s), 4);
+      mbar_init(bar(B_DFULL + s), 2);
+    }
+    for (int b = 0; b < TL_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TL_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TL_MMA_WARPS); }
+    for (int st = 0; st < TL_CONV_WARPS * TL_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_base_s != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
+
+  if (warp >= W_MMA) {
+    // =========================== MMA issuers: two warps per sub-tile ==================================
+    const int s = (warp - W_MMA) >> 1, role = (warp - W_MMA) & 1;
+    const bool leader = elect_one();
+    tc_fence_before();
+    __syncthreads();                                   // weights in TMEM, h_{-1} / x_0 tiles under way
+    tc_fence_after();
+    const int nkx = KI >> 4;
+    const bool x_has_lo = d.x_dtype != FGRNN_BF16;
+    const uint64_t dHhi = make_desc_mn(smem_u32(sm + L.h_op + s * 2 * TL_H_TILE), TL_NS), dHlo = dHhi + (TL_H_TILE >> 4);
+    const uint64_t dShi = make_desc_mn(smem_u32(sm + L.s_op + s * 2 * TL_S_TILE), TL_NS), dSlo = dShi + (TL_S_TILE >> 4);
+    const uint64_t dX0 = tl_desc_kmajor(smem_u32(sm + L.x_op), KI);
+    const uint32_t xlo_step = (uint32_t)L.x_tile_bytes >> 4, xtile_step = 2 * xlo_step, xbuf_step = TL_NT * xtile_step;
+    const uint32_t acc1 = tmem + TLM_ACC + s * 64 + role * TL_NS;           // D1: X (role 0) | Y (role 1);  D2: tile `role`
+    const uint32_t a2hi = tmem + TLM_A2 + role * 48, a2lo = a2hi + 24;
+    if (s) tc_spin_ns(TL_STAGGER_NS);                  // the second sub-tile starts half a period behind the first
+    for (int t = 0; t < d.T; ++t) {
+      const int xb = t % TL_XBUF;
+      mbar_wait(bar(B_XFULL + xb), (t / TL_XBUF) & 1); // x_t operand tiles written
+      mbar_wait(bar(B_HREADY + s), t & 1);             // h_{t-1} operand tile written, D2 of step t-1 drained
+      tc_fence_after();
+      if (leader) {
+        // ---- stage 1.  Every accumulator: lo products first, then hi.hi (the header explains why) ----
+        if (role == 0) {
+          const uint64_t dXhi = dX0 + (uint64_t)(xb * xbuf_step + s * xtile_step), dXlo = dXhi + xlo_step;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            umma_ts1(acc1, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 0);
+            umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+          }
+          for (int ks = 0; ks < nkx; ++ks) {
+            umma_ts1(acc1, tmem + TLM_A1X_LO + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
+            if (x_has_lo) umma_ts1(acc1, tmem + TLM_A1X_HI + ks * 8, dXlo + ks * TL_X_KSTEP, TL_IDESC_X, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+          for (int ks = 0; ks < nkx; ++ks) umma_ts1(acc1, tmem + TLM_A1X_HI + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
+        } else {
+#pragma unroll
+          for (int ks = 8; ks < 16; ++ks) {
+            umma_ts1(acc1, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 8);
+            umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+          }
+#pragma unroll
+          for (int ks = 8; ks < 16; ++ks) umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+        }
+        umma_commit1(bar(B_D1FULL + s));
+        umma_commit1(bar(B_XEMPTY + xb));              // this warp's MMAs have consumed the x_t tiles
+      }
+      __syncwarp();
+      mbar_wait(bar(B_SREADY + s), t & 1);             // s tile written, D1 drained
+      tc_fence_after();
+      if (leader) {
+        // ---- stage 2, unit tile `role`: K = 48 ----
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+          umma_ts1(acc1, a2lo + ks * 8, dShi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 0);
+          umma_ts1(acc1, a2hi + ks * 8, dSlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) umma_ts1(acc1, a2hi + ks * 8, dShi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+        umma_commit1(bar(B_DFULL + s));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= W_CONV0) {
+    // =========================== x path: TMA -> fp16 hi/lo split -> K-major operand tiles (as fgrnn_tc.cu) ========
+    const int cw = warp - W_CONV0;
+    const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
+    unsigned char* raw_base = sm + L.raw + cw * TL_RAW_STAGES * L.raw_stage_bytes;
+    const int my_row0 = row0 + cw * TL_CONV_ROWS;
+    auto issue_tma = [&](int t) {
+      const int st = t % TL_RAW_STAGES;
+      const uint32_t fb = bar(B_RAWFULL + cw * TL_RAW_STAGES + st);
+      mbar_expect_tx(fb, raw_bytes);
+      if (ta.x_time_outer) tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, my_row0, t, fb);
+      else tma_load_3d(smem_u32(raw_base + st * L.raw_stage_bytes), &xmap, 0, t, my_row0, fb);
+    };
+    if (lane == 0)
+      for (int t = 0; t < TL_RAW_STAGES && t < d.T; ++t) issue_tma(t);
+    tc_fence_before();
+    __syncthreads();
+    const int nch = KI >> 3, ntask = TL_CONV_ROWS * nch;          // <= 64 tasks: at most 2 per lane
+    constexpr int MAXIT = TL_CONV_ROWS * (TL_MAX_KI / 8) / 32;
+    uint32_t src_off[MAXIT], dst_off[MAXIT];
+    bool live[MAXIT], pad[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int e = it * 32 + lane;
+      const int row = e / nch, ch = e - row * nch;
+      live[it] = e < ntask;
+      pad[it] = ch * 8 >= I;
+      src_off[it] = (uint32_t)(row * I * esz + ch * 8 * esz);
+      const int R = cw * TL_CONV_ROWS + row, sidx = R / TL_NS, r = R - sidx * TL_NS;
+      dst_off[it] = (uint32_t)((sidx * 2) * L.x_tile_bytes + (r >> 3) * (nch * 128) + ch * 128 + (r & 7) * 16);
+    }
+    const uint32_t xbuf_bytes = (uint32_t)(TL_NT * 2 * L.x_tile_bytes);
+    for (int t = 0; t < d.T; ++t) {
+      const int st = t % TL_RAW_STAGES, xb = t % TL_XBUF;
+      mbar_wait(bar(B_RAWFULL + cw * TL_RAW_STAGES + st), (t / TL_RAW_STAGES) & 1);
+      mbar_wait(bar(B_XEMPTY + xb), ((t / TL_XBUF) & 1) ^ 1);    // MMAs of step t - XBUF have finished with this buffer
+      const unsigned char* raw = raw_base + st * L.raw_stage_bytes;
+      unsigned char* xdst = sm + L.x_op + xb * xbuf_bytes;
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        if (live[it]) {
+          float v[8];
+          if (!pad[it]) {
+            if (esz == 4) {
+              const float4 p0 = *reinterpret_cast<const float4*>(raw + src_off[it]);
+              const float4 p1 = *reinterpret_cast<const float4*>(raw + src_off[it] + 16);
+              v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+            } else {
+              const uint4 p = *reinterpret_cast<const uint4*>(raw + src_off[it]);
+              const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], 1.0f, hi[q], lo[q]);
+          *reinterpret_cast<uint4*>(xdst + dst_off[it]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(xdst + dst_off[it] + L.x_tile_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(B_XFULL + xb));
+        if (t + TL_RAW_STAGES < d.T) issue_tma(t + TL_RAW_STAGES);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue warps ===================================================
+    const int ew = warp;                               // 0..15
+    const int quad = ew & 3;                           // TMEM lane quadrant
+    const int es = (ew >> 2) & 1;                      // sub-tile
+    const int m = ew >> 3;                             // unit tile (and, for the hop, the row half)
+    const int part = ew >> 2;                          // 0..3: share of the weight upload
+    const int ln = quad * 32 + lane;                   // TMEM lane
+    const int gu = m * 128 + ln;                       // hidden unit of this thread
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+
+    // ---- power-of-two scales from max |U1|, |W1| (stage 1) and max |U2|, |W2| (stage 2); largest bias distance
+    float m1 = 0.f, m2 = 0.f;
+    {
+      const int et = ew * 32 + lane, nthr = TL_EPI_WARPS * 32;
+      for (int i = et; i < TL_H * rU; i += nthr) { m1 = fmaxf(m1, fabsf(__ldg(a.U1c + i))); m2 = fmaxf(m2, fabsf(__ldg(a.U2c + i))); }
+      for (int i = et; i < I * rW; i += nthr) m1 = fmaxf(m1, fabsf(__ldg(a.W1c + i)));
+      for (int i = et; i < rW * TL_H; i += nthr) m2 = fmaxf(m2, fabsf(__ldg(a.W2c + i)));
+    }
+    float bd = es == 0 ? fabsf(__ldg(a.bias_gate + gu) - __ldg(a.bias_update + gu)) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      bd = fmaxf(bd, __shfl_xor_sync(0xffffffffu, bd, o));
+    }
+    if (lane == 0) { red_s[ew] = m1; red_s[16 + ew] = m2; red_s[32 + ew] = bd; }
+    asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_WARPS * 32) : "memory");      // epilogue warps only
+#pragma unroll
+    for (int w = 0; w < TL_EPI_WARPS; ++w) { m1 = fmaxf(m1, red_s[w]); m2 = fmaxf(m2, red_s[16 + w]); bd = fmaxf(bd, red_s[32 + w]); }
+    const bool wide_bias = !(bd <= 8.0f);
+    int S1 = 40, S2 = 40;
+    if (m1 > 0.f) S1 = min(S1, (int)floorf(log2f(30000.f / m1)));
+    if (m2 > 0.f) S2 = min(S2, (int)floorf(log2f(30000.f / m2)));
+    S1 = max(S1, -14); S2 = max(S2, -14);
+    const float scale1 = exp2f((float)S1), unscale1 = exp2f((float)-S1);
+    const float scale2 = exp2f((float)S2), unscale2 = exp2f((float)-S2);
+
+    // ---- stage-1 weights -> tensor memory.  A1[lane = rank row][k]: lanes 0..31 = U1^T (k = hidden unit), lanes
+    //      32..47 = W1^T (k = input feature, its own columns), everything else zero (block diagonal).
+    for (int kb = part; kb < 16; kb += 4) {              // h part: 16 k-blocks of 16 units
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = kb * 16 + 2 * j;
+        const float v0 = (quad == 0 && lane < rU) ? __ldg(a.U1c + (size_t)k * rU + lane) : 0.f;
+        const float v1 = (quad == 0 && lane < rU) ? __ldg(a.U1c + (size_t)(k + 1) * rU + lane) : 0.f;
+        split2(v0, v1, scale1, hi[j], lo[j]);
+      }
+      tmem_st8(tmem + lane_base + TLM_A1_HI + kb * 8, hi);
+      tmem_st8(tmem + lane_base + TLM_A1_LO + kb * 8, lo);
+    }
+    if (part < 2) {                                      // x part: 2 k-blocks of 16 features
+      const int kb = part;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = kb * 16 + 2 * j;
+        const float v0 = (quad == 1 && lane < rW && k < I) ? __ldg(a.W1c + (size_t)k * rW + lane) : 0.f;
+        const float v1 = (quad == 1 && lane < rW && k + 1 < I) ? __ldg(a.W1c + (size_t)(k + 1) * rW + lane) : 0.f;
+        split2(v0, v1, scale1, hi[j], lo[j]);
+      }
+      tmem_st8(tmem + lane_base + TLM_A1X_HI + kb * 8, hi);
+      tmem_st8(tmem + lane_base + TLM_A1X_LO + kb * 8, lo);
+    }
+    // ---- stage-2 weights: A2[tile][lane = unit][j]: j < 32 -> U2[j][unit], 32 <= j < 48 -> W2[j - 32][unit]
+    {
+      const int tile = part & 1, unit = tile * 128 + ln;
+      const int kb0 = (part >> 1) ? 2 : 0, kb1 = (part >> 1) ? 3 : 2;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = kb * 16 + 2 * j + e;
+            v[e] = k < TL_RU ? (k < rU ? __ldg(a.U2c + (size_t)k * TL_H + unit) : 0.f)
+                             : (k - TL_RU < rW ? __ldg(a.W2c + (size_t)(k - TL_RU) * TL_H + unit) : 0.f);
+          }
+          split2(v[0], v[1], scale2, hi[j], lo[j]);
+        }
+        tmem_st8(tmem + lane_base + TLM_A2 + tile * 48 + kb * 8, hi);
+        tmem_st8(tmem + lane_base + TLM_A2 + tile * 48 + 24 + kb * 8, lo);
+      }
+    }
+    tmem_st_wait();
+
+    // ---- per-unit constants of the gate update
+    TlEpiConst kc;
+    bool one_ex2;
+    {
+      const float sz = sigmoid_f(__ldg(a.zeta)), sn = sigmoid_f(__ldg(a.nu));
+      constexpr float LOG2E = 1.4426950408889634f;
+      const float bgv = __ldg(a.bias_gate + gu), buv = __ldg(a.bias_update + gu);
+      const float kS = -LOG2E * unscale2, cg = -LOG2E * bgv;
+      kc.kS = make_float2(kS, kS); kc.cg = make_float2(cg, cg);
+      kc.msz = make_float2(-sz, -sz); kc.szn = make_float2(sz + sn, sz + sn);
+      const float k2S = -2.0f * LOG2E * unscale2, cu2 = -2.0f * LOG2E * buv;
+      kc.k2S = make_float2(k2S, k2S); kc.cu2 = make_float2(cu2, cu2);
+      one_ex2 = !wide_bias;
+      const float ratio = one_ex2 ? expf(2.0f * (bgv - buv)) : 1.0f;
+      kc.cu = make_float2(ratio, ratio);
+      kc.tmin = (30.0f - cg) / kS;
+    }
+
+    // ---- state: h[row][gu] for the 32 rows of this sub-tile; h_{-1} operand tile
+    float2 hst[TL_NS / 2];
+    unsigned char* hop = sm + L.h_op + es * (2 * TL_H_TILE) + (gu >> 3) * ((TL_NS >> 3) * 128) + (gu & 7) * 16;
+    const int first_row = row0 + es * TL_NS;
+#pragma unroll
+    for (int g = 0; g < TL_NS / 8; ++g) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = first_row + g * 8 + 2 * q;
+        const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TL_H + gu) : 0.f;
+        const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TL_H + gu) : 0.f;
+        hst[g * 4 + q] = make_float2(v0, v1);
+        split2(v0, v1, 1.0f, hi[q], lo[q]);
+      }
+      *reinterpret_cast<uint4*>(hop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(hop + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();                                   // matches the other roles' prologue barrier
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(B_HREADY + es));    // phase 0: h_{-1} ready
+
+    TlEpiCtx cx;
+    cx.bar_d1full = bar(B_D1FULL + es); cx.bar_sready = bar(B_SREADY + es);
+    cx.bar_dfull = bar(B_DFULL + es); cx.bar_hready = bar(B_HREADY + es);
+    cx.hopper = quad < 2;
+    cx.d1 = tmem + lane_base + TLM_ACC + es * 64 + m * 16;
+    cx.d2 = tmem + lane_base + TLM_ACC + es * 64 + m * TL_NS;
+    cx.sop = nullptr;
+    if (quad < 2 && ln < TL_K2)                          // rank row ln of D1 = k index ln of the stage-2 operand; rows m*16 ..
+      cx.sop = sm + L.s_op + es * (2 * TL_S_TILE) + (ln >> 3) * ((TL_NS >> 3) * 128) + (m * 2) * 128 + (ln & 7) * 16;
+    cx.hop = hop;
+    cx.out = a.out ? a.out + (size_t)first_row * a.osb + gu : nullptr;
+    cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost;
+    cx.rows_left = d.B - first_row; cx.T = d.T; cx.unscale1 = unscale1;
+    const bool masked = row0 + TL_ROWS > d.B;
+    const int variant = (one_ex2 ? 4 : 0) | (a.out ? 2 : 0) | (masked ? 1 : 0);
+    switch (variant) {
+      case 0: tl_epilogue_loop<false, false, false>(cx, kc, hst); break;
+      case 1: tl_epilogue_loop<false, true, false>(cx, kc, hst); break;
+      case 2: tl_epilogue_loop<true, false, false>(cx, kc, hst); break;
+      case 3: tl_epilogue_loop<true, true, false>(cx, kc, hst); break;
+      case 4: tl_epilogue_loop<false, false, true>(cx, kc, hst); break;
+      case 5: tl_epilogue_loop<false, true, true>(cx, kc, hst); break;
+      case 6: tl_epilogue_loop<true, false, true>(cx, kc, hst); break;
+      default: tl_epilogue_loop<true, true, true>(cx, kc, hst); break;
+    }
+    if (a.h_last) {
+#pragma unroll
+      for (int j = 0; j < TL_NS; ++j) {
+        const int row = first_row + j;
+        if (row < d.B) a.h_last[(size_t)row * TL_H + gu] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool tc_lr_supports(const Dims& d) {
+  return d.H == TL_H && d.rU > 0 && d.rU <= TL_RU && d.rW > 0 && d.rW <= TL_RW && d.I >= 8 && d.I <= TL_MAX_KI && (d.I % 8) == 0 &&
+         d.gate_nl == FGRNN_NL_SIGMOID && d.update_nl == FGRNN_NL_TANH;
+}
+
+int launch_tc_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
+  const Dims& d = a.d;
+  if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
+  TlArgs ta{};
+  ta.f = a;
+  ta.KI = (d.I + 15) & ~15;
+  const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
+  CUtensorMap map;
+  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, TL_CONV_ROWS, &ta.x_time_outer);
+  if (rc) return rc;
+  const TlSmem L = tl_smem_layout(d.I, ta.KI, esz);
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_lr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const unsigned grid = (unsigned)((d.B + TL_ROWS - 1) / TL_ROWS);
+  tc_lr_fwd_kernel<<<grid, TL_THREADS, L.total, stream>>>(ta, map);
+  FGRNN_LAUNCH_CHECK("tc_lr_fwd_kernel");
+  return FGRNN_OK;
+}
+
+}  // namespace fgrnn

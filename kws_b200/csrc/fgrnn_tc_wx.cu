@@ -624,14 +624,14 @@ struct TcWxFwd {
                 // sigmoid gate: one MUFU.RCP serves both gates (fgrnn_tc.cu): r = 1 / ((1 + e_g)(1 + e_u))
                 float2 eg, eu;
                 if (MODE == 0) {
-                  const float2 pc = make_float2(fmaxf(pre.x, kc.tmin), fmaxf(pre.y, kc.tmin));
+                  const float2 pc = make_float2(fmax_nan(pre.x, kc.tmin), fmax_nan(pre.y, kc.tmin));
                   const float2 ag = __ffma2_rn(pc, kc.kg, kc.cg);
                   eg = make_float2(ex2_approx(ag.x), ex2_approx(ag.y));
                   eu = __fmul2_rn(__fmul2_rn(eg, eg), kc.cu);
                 } else {
                   float2 ag = __ffma2_rn(pre, kc.kg, kc.cg), au = __ffma2_rn(pre, kc.ku, kc.cu);
-                  ag.x = fminf(ag.x, 60.0f); ag.y = fminf(ag.y, 60.0f);
-                  au.x = fminf(au.x, 60.0f); au.y = fminf(au.y, 60.0f);
+                  ag.x = fmin_nan(ag.x, 60.0f); ag.y = fmin_nan(ag.y, 60.0f);
+                  au.x = fmin_nan(au.x, 60.0f); au.y = fmin_nan(au.y, 60.0f);
                   eg = make_float2(ex2_approx(ag.x), ex2_approx(ag.y)); eu = make_float2(ex2_approx(au.x), ex2_approx(au.y));
                 }
                 const float2 ga = __fadd2_rn(eg, one), ub = __fadd2_rn(eu, one);

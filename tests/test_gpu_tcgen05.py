@@ -243,3 +243,24 @@ def test_tcgen05_backward_with_bf16_inputs():
     torch.cuda.synchronize()
     for k in p.tensors():
         assert grad_ratio(g[k], gref[k]) <= 1.0, (k, grad_ratio(g[k], gref[k]))
+
+
+@pytest.mark.parametrize("I,H", [(32, 128), (64, 256)])
+def test_tcgen05_nan_input_poisons_its_own_row_only(I, H):
+    """A NaN feature makes that row's states NaN from its step on (as rnn.py does) -- the activation clamps keep NaN
+    (max.NaN / min.NaN) -- and leaves the other rows of the tile untouched."""
+    from kws_b200 import engine
+    torch.manual_seed(4)
+    p = O.init_params(I, H)
+    x = torch.randn(64, 5, I)
+    ref = O.unroll(x, p, None, True)
+    xg = x.to(dev()); xg[9, 2, 1] = float("nan")
+    params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+    assert engine.forward_plan(xg, params, None, layout="IH", batch_first=True) == "tcgen05"
+    out = engine.forward(xg, params, None, layout="IH", batch_first=True)[0]
+    torch.cuda.synchronize()
+    assert torch.isnan(out[9, 2:]).all() and torch.isfinite(out[9, :2]).all()
+    keep = [r for r in range(64) if r != 9]
+    assert torch.isfinite(out[keep]).all()
+    if I + H < 320:
+        assert state_ratio(out[keep], ref[keep]) <= 1.0
