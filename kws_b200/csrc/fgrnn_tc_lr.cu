@@ -9,6 +9,12 @@
 //   stage 2   D2^T[unit][row] = [U2^T | W2^T] . [s ; sx]              two M = 128 tiles (256 units), K = 48, N = 32
 //   epilogue  gate update (rnn.py:289-295) exactly as fgrnn_tc.cu: thread = hidden unit, 32 rows, h in registers
 //
+// Warp roles (24 warps): 0..15 epilogue -- ALL of them serve both sub-tiles in turn (thread = hidden unit x 16 rows of
+// each sub-tile), so that a sub-tile's epilogue has four warps per scheduler behind it: the per-step chain of a sub-tile
+// (stage 1 -> hop -> stage 2 -> epilogue) is what bounds the kernel, and with eight warps per sub-tile the epilogue alone
+// was half of it (tools/trace_lowrank.py); 16..17 hop (lane quadrants 0 and 1, no global stores in flight when they
+// fence); 18..19 x path (TMA -> fp16 split, one sub-tile each); 20..23 MMA issue ([sub-tile][role]).
+//
 // Both weight sets stay in TENSOR MEMORY for the whole kernel (fp16 hi/lo pairs): stage 1 takes 288 columns, stage 2
 // 96, which leaves 128 columns = 64 per sub-tile.  D1 and D2 of a sub-tile are never live at the same time (D1 dies when
 // the hop has read it, D2 when the epilogue has read it), so they ALIAS: two sub-tiles of 32 rows per CTA run half a
@@ -27,8 +33,9 @@ namespace fgrnn {
 
 constexpr int TL_H = 256, TL_NS = 32, TL_NT = 2, TL_ROWS = TL_NS * TL_NT;
 constexpr int TL_RU = 32, TL_RW = 16, TL_K2 = TL_RU + TL_RW;            // padded ranks; K of stage 2
-constexpr int TL_EPI_WARPS = 16, TL_CONV_WARPS = 4, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
-constexpr int TL_THREADS = 32 * (TL_EPI_WARPS + TL_CONV_WARPS + TL_MMA_WARPS);
+constexpr int TL_EPI_WARPS = 16, TL_HOP_WARPS = 2, TL_CONV_WARPS = 2, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
+constexpr int TL_THREADS = 32 * (TL_EPI_WARPS + TL_HOP_WARPS + TL_CONV_WARPS + TL_MMA_WARPS);
+constexpr int TL_RPT = TL_NS / 2;                     // rows of each sub-tile per epilogue thread
 constexpr int TL_XBUF = 4, TL_RAW_STAGES = 4, TL_CONV_ROWS = TL_ROWS / TL_CONV_WARPS;
 constexpr int TL_MAX_KI = 32;
 // tensor-memory column map
@@ -39,6 +46,21 @@ constexpr int TL_H_TILE = TL_H * TL_NS * 2;           // one fp16 [256][32] oper
 constexpr int TL_S_TILE = TL_K2 * TL_NS * 2;          // one fp16 [48][32] operand tile: 3 KB
 #ifndef TL_STAGGER_NS
 #define TL_STAGGER_NS 900
+#endif
+
+// Developer trace (make trace -> -DFGRNN_TL_TRACE): clock64 stamps of CTA 0 for steps [16, 24), per sub-tile:
+//   0 MMA role 0: HREADY seen   1 stage 1 issued   2 SREADY seen   3 stage 2 issued
+//   4 hop warp 0: D1FULL seen   5 SREADY arrive    6 epilogue warp 0: DFULL seen   7 HREADY arrive   8 stores issued
+//   9 epilogue warp 15: DFULL seen    10 its HREADY arrive
+#ifdef FGRNN_TL_TRACE
+__device__ long long g_tl_trace[8 * 2 * 16];
+#define TL_TRACE(t, s, slot)                                                                         \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) >= 16 && (t) < 24)                         \
+      g_tl_trace[(((t) - 16) * 2 + (s)) * 16 + (slot)] = clock64();                                  \
+  } while (0)
+#else
+#define TL_TRACE(t, s, slot) do { } while (0)
 #endif
 
 struct TlArgs {
@@ -100,80 +122,89 @@ static __device__ __forceinline__ float2 tl_gate_update2(float2 tot, float2 h, c
 }
 
 struct TlEpiCtx {
-  uint32_t bar_d1full, bar_sready, bar_dfull, bar_hready;
-  uint32_t d1;                        // TMEM address of this warp's 16 columns of D1.X (hop warps)
-  uint32_t d2;                        // TMEM address of this thread's unit in D2 (32 columns)
-  unsigned char* sop;                 // s operand tile address of (k = this lane's rank row, row group 2m), hi part; null = no store
-  unsigned char* hop;                 // h operand tile address of (k = unit, row group 0), hi part
-  float* out; uint32_t out_row, out_step;
-  int rows_left, T;
-  bool hopper;                        // this warp takes part in the hop (lane quadrants 0 and 1)
-  float unscale1;
+  uint32_t bar_dfull, bar_hready;     // shared addresses of the [NT] barrier arrays (sub-tile s: + 8 s)
+  uint32_t d2;                        // TMEM address of this thread's unit in D2 of sub-tile 0, its 16 columns (sub-tile s: + 64 s)
+  unsigned char* hop;                 // h operand tile address of (sub-tile 0, k = unit, this thread's first row group), hi part
+  float* out; uint32_t out_row, out_step;      // &out[first row of sub-tile 0][t = 0][unit]; element strides
+  int rows_left, T, tr;               // rows_left: B - first row (sub-tile 0); tr: trace role
 };
 
+// Epilogue main loop of one warp: thread = hidden unit; rows [rh*16, rh*16 + 16) of sub-tile 0, then of sub-tile 1.
 template <bool HAS_OUT, bool MASKED, bool ONE_EX2>
-static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, const TlEpiConst& kc, float2 (&hst)[TL_NS / 2]) {
+static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, const TlEpiConst& kc, float2 (&hst)[TL_NT][TL_RPT / 2]) {
   char* outp = reinterpret_cast<char*>(cx.out);
   const uint32_t row_bytes = cx.out_row * 4u;
   for (int t = 0; t < cx.T; ++t) {
-    if (cx.hopper) {
-      // ---- hop: D1 (rank rows) -> fp16 hi/lo B operand of stage 2 -----------------------------------
-      mbar_wait(cx.bar_d1full, t & 1);
+#pragma unroll
+    for (int s = 0; s < TL_NT; ++s) {
+      mbar_wait(cx.bar_dfull + 8 * s, t & 1);
       tc_fence_after();
-      float vx[16], vy[16];
-      tmem_ld16(cx.d1, vx);
-      tmem_ld16(cx.d1 + TL_NS, vy);
-      tmem_ld_wait();
-      if (cx.sop) {
+      if (cx.tr == 1) TL_TRACE(t, s, 6);
+      if (cx.tr == 2) TL_TRACE(t, s, 9);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint32_t hi[4], lo[4];
+      for (int g = 0; g < TL_RPT / 8; ++g) {
+        float v[8];
+        tmem_ld8(cx.d2 + s * 64 + g * 8, v);
+        tmem_ld_wait();
+        uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            split2(vx[g * 8 + 2 * q] + vy[g * 8 + 2 * q], vx[g * 8 + 2 * q + 1] + vy[g * 8 + 2 * q + 1], cx.unscale1, hi[q], lo[q]);
-          *reinterpret_cast<uint4*>(cx.sop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(cx.sop + TL_S_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int q = 0; q < 4; ++q) {
+          const int p = g * 4 + q;
+          hst[s][p] = tl_gate_update2<ONE_EX2>(make_float2(v[2 * q], v[2 * q + 1]), hst[s][p], kc);
+          const __half2 hh = __float22half2_rn(hst[s][p]);
+          const float2 hf = __half22float2(hh);
+          const __half2 hl = __float22half2_rn(__fadd2_rn(hst[s][p], make_float2(-hf.x, -hf.y)));
+          hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[q] = *reinterpret_cast<const uint32_t*>(&hl);
+        }
+        *reinterpret_cast<uint4*>(cx.hop + s * (2 * TL_H_TILE) + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(cx.hop + s * (2 * TL_H_TILE) + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();                        // st.shared of the h tile -> visible to tcgen05.mma
+      tc_fence_before();                               // tcgen05.ld of D2 done before stage 1 of the next step overwrites it
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + 8 * s);
+      if (cx.tr == 1) TL_TRACE(t, s, 7);
+      if (cx.tr == 2) TL_TRACE(t, s, 10);
+      if (HAS_OUT) {
+        char* o = outp + (uint32_t)(s * TL_NS) * row_bytes;
+#pragma unroll
+        for (int q = 0; q < TL_RPT / 2; ++q) {
+          if (!MASKED || s * TL_NS + 2 * q < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q) * row_bytes) = hst[s][q].x;
+          if (!MASKED || s * TL_NS + 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q + 1) * row_bytes) = hst[s][q].y;
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_sready);
+      if (cx.tr == 1) TL_TRACE(t, s, 8);
     }
-    // ---- D2 -> gate update -> h_t ----------------------------------------------------------------------
-    mbar_wait(cx.bar_dfull, t & 1);
-    tc_fence_after();
+    if (HAS_OUT) outp += (size_t)cx.out_step * 4u;
+  }
+}
+
+// Stage 1 of one sub-tile step, straight-line on the elected lane.  Every accumulator takes its lo products first and its
+// hi.hi products after them (see the header):
+//   role 0 -> X: lo of h k-steps 0..7, lo of x, hi.hi of h k-steps 0..7, hi.hi of x        (the x part lands in lanes 32..47)
+//   role 1 -> Y: lo of h k-steps 8..15, hi.hi of h k-steps 8..15
+template <int ROLE, int NKX, bool X_HAS_LO>
+static __device__ __forceinline__ void tl_issue_stage1(uint32_t acc, uint64_t dHhi, uint64_t dHlo, uint64_t dXhi, uint64_t dXlo) {
+  constexpr uint32_t tmem = 0u;
+  constexpr int k0 = ROLE * 8;
 #pragma unroll
-    for (int g = 0; g < TL_NS / 8; ++g) {
-      float v[8];
-      tmem_ld8(cx.d2 + g * 8, v);
-      tmem_ld_wait();
-      uint32_t hi[4], lo[4];
+  for (int ks = k0; ks < k0 + 8; ++ks) {
+    umma_ts1(acc, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > k0);
+    umma_ts1(acc, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+  }
+  if (ROLE == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int p = g * 4 + q;
-        hst[p] = tl_gate_update2<ONE_EX2>(make_float2(v[2 * q], v[2 * q + 1]), hst[p], kc);
-        const __half2 hh = __float22half2_rn(hst[p]);
-        const float2 hf = __half22float2(hh);
-        const __half2 hl = __float22half2_rn(__fadd2_rn(hst[p], make_float2(-hf.x, -hf.y)));
-        hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
-        lo[q] = *reinterpret_cast<const uint32_t*>(&hl);
-      }
-      *reinterpret_cast<uint4*>(cx.hop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(cx.hop + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    for (int ks = 0; ks < NKX; ++ks) {
+      umma_ts1(acc, tmem + TLM_A1X_LO + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
+      if (X_HAS_LO) umma_ts1(acc, tmem + TLM_A1X_HI + ks * 8, dXlo + ks * TL_X_KSTEP, TL_IDESC_X, 1);
     }
-    fence_proxy_async_smem();                          // st.shared of the h tile -> visible to tcgen05.mma
-    tc_fence_before();                                 // tcgen05.ld of D2 done before stage 1 of the next step overwrites it
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready);
-    if (HAS_OUT) {
+  }
 #pragma unroll
-      for (int q = 0; q < TL_NS / 2; ++q) {
-        if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
-        if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
-      }
-      outp += (size_t)cx.out_step * 4u;
-    }
+  for (int ks = k0; ks < k0 + 8; ++ks) umma_ts1(acc, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+  if (ROLE == 0) {
+#pragma unroll
+    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc, tmem + TLM_A1X_HI + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
   }
 }
 
@@ -186,20 +217,20 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
   const TlSmem L = tl_smem_layout(I, KI, esz);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
-  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16]
+  float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16] reduction scratch, [48] = 2^-S1 for the hop warps
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int row0 = blockIdx.x * TL_ROWS;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   // per sub-tile: HREADY (h_{t-1} tile written, D2 drained) | D1FULL | SREADY (s tile written, D1 drained) | DFULL
   const int B_HREADY = 0, B_D1FULL = 2, B_SREADY = 4, B_DFULL = 6, B_XFULL = 8, B_XEMPTY = 12, B_RAWFULL = 16;
-  constexpr int W_CONV0 = TL_EPI_WARPS, W_MMA = TL_EPI_WARPS + TL_CONV_WARPS;
+  constexpr int W_HOP0 = TL_EPI_WARPS, W_CONV0 = W_HOP0 + TL_HOP_WARPS, W_MMA = W_CONV0 + TL_CONV_WARPS;
 
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), 512);
   if (tid == 0) {
     for (int s = 0; s < TL_NT; ++s) {
-      mbar_init(bar(B_HREADY + s), TL_EPI_WARPS / TL_NT);
+      mbar_init(bar(B_HREADY + s), TL_EPI_WARPS);
       mbar_init(bar(B_D1FULL + s), 2);
-      mbar_init(bar(B_SREADY + s), 4);
+      mbar_init(bar(B_SREADY + s), TL_HOP_WARPS);
       mbar_init(bar(B_DFULL + s), 2);
     }
     for (int b = 0; b < TL_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TL_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TL_MMA_WARPS); }
@@ -227,45 +258,33 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     const uint32_t xlo_step = (uint32_t)L.x_tile_bytes >> 4, xtile_step = 2 * xlo_step, xbuf_step = TL_NT * xtile_step;
     const uint32_t acc1 = tmem + TLM_ACC + s * 64 + role * TL_NS;           // D1: X (role 0) | Y (role 1);  D2: tile `role`
     const uint32_t a2hi = tmem + TLM_A2 + role * 48, a2lo = a2hi + 24;
+    const int variant = role ? 4 : (nkx - 1) * 2 + (x_has_lo ? 1 : 0);
     if (s) tc_spin_ns(TL_STAGGER_NS);                  // the second sub-tile starts half a period behind the first
     for (int t = 0; t < d.T; ++t) {
       const int xb = t % TL_XBUF;
       mbar_wait(bar(B_XFULL + xb), (t / TL_XBUF) & 1); // x_t operand tiles written
       mbar_wait(bar(B_HREADY + s), t & 1);             // h_{t-1} operand tile written, D2 of step t-1 drained
       tc_fence_after();
+      if (role == 0) TL_TRACE(t, s, 0);
       if (leader) {
-        // ---- stage 1.  Every accumulator: lo products first, then hi.hi (the header explains why) ----
-        if (role == 0) {
-          const uint64_t dXhi = dX0 + (uint64_t)(xb * xbuf_step + s * xtile_step), dXlo = dXhi + xlo_step;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            umma_ts1(acc1, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 0);
-            umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
-          }
-          for (int ks = 0; ks < nkx; ++ks) {
-            umma_ts1(acc1, tmem + TLM_A1X_LO + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
-            if (x_has_lo) umma_ts1(acc1, tmem + TLM_A1X_HI + ks * 8, dXlo + ks * TL_X_KSTEP, TL_IDESC_X, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
-          for (int ks = 0; ks < nkx; ++ks) umma_ts1(acc1, tmem + TLM_A1X_HI + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
-        } else {
-#pragma unroll
-          for (int ks = 8; ks < 16; ++ks) {
-            umma_ts1(acc1, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 8);
-            umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
-          }
-#pragma unroll
-          for (int ks = 8; ks < 16; ++ks) umma_ts1(acc1, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+        const uint64_t dXhi = dX0 + (uint64_t)(xb * xbuf_step + s * xtile_step), dXlo = dXhi + xlo_step;
+        switch (variant) {
+          case 0: tl_issue_stage1<0, 1, false>(acc1, dHhi, dHlo, dXhi, dXlo); break;
+          case 1: tl_issue_stage1<0, 1, true>(acc1, dHhi, dHlo, dXhi, dXlo); break;
+          case 2: tl_issue_stage1<0, 2, false>(acc1, dHhi, dHlo, dXhi, dXlo); break;
+          case 3: tl_issue_stage1<0, 2, true>(acc1, dHhi, dHlo, dXhi, dXlo); break;
+          default: tl_issue_stage1<1, 0, false>(acc1, dHhi, dHlo, dXhi, dXlo); break;
         }
         umma_commit1(bar(B_D1FULL + s));
         umma_commit1(bar(B_XEMPTY + xb));              // this warp's MMAs have consumed the x_t tiles
       }
       __syncwarp();
+      if (role == 0) TL_TRACE(t, s, 1);
       mbar_wait(bar(B_SREADY + s), t & 1);             // s tile written, D1 drained
       tc_fence_after();
+      if (role == 0) TL_TRACE(t, s, 2);
       if (leader) {
-        // ---- stage 2, unit tile `role`: K = 48 ----
+        // ---- stage 2, unit tile `role`: K = 48; lo products first ----
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) {
           umma_ts1(acc1, a2lo + ks * 8, dShi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > 0);
@@ -276,9 +295,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
         umma_commit1(bar(B_DFULL + s));
       }
       __syncwarp();
+      if (role == 0) TL_TRACE(t, s, 3);
     }
   } else if (warp >= W_CONV0) {
-    // =========================== x path: TMA -> fp16 hi/lo split -> K-major operand tiles (as fgrnn_tc.cu) ========
+    // =========================== x path: TMA -> fp16 hi/lo split -> K-major operand tiles =========================
+    // converter warp cw owns sub-tile cw: 32 rows, one TMA box per step, a private raw ring
     const int cw = warp - W_CONV0;
     const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
     unsigned char* raw_base = sm + L.raw + cw * TL_RAW_STAGES * L.raw_stage_bytes;
@@ -294,7 +315,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       for (int t = 0; t < TL_RAW_STAGES && t < d.T; ++t) issue_tma(t);
     tc_fence_before();
     __syncthreads();
-    const int nch = KI >> 3, ntask = TL_CONV_ROWS * nch;          // <= 64 tasks: at most 2 per lane
+    const int nch = KI >> 3, ntask = TL_CONV_ROWS * nch;          // <= 128 tasks: at most 4 per lane
     constexpr int MAXIT = TL_CONV_ROWS * (TL_MAX_KI / 8) / 32;
     uint32_t src_off[MAXIT], dst_off[MAXIT];
     bool live[MAXIT], pad[MAXIT];
@@ -305,8 +326,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       live[it] = e < ntask;
       pad[it] = ch * 8 >= I;
       src_off[it] = (uint32_t)(row * I * esz + ch * 8 * esz);
-      const int R = cw * TL_CONV_ROWS + row, sidx = R / TL_NS, r = R - sidx * TL_NS;
-      dst_off[it] = (uint32_t)((sidx * 2) * L.x_tile_bytes + (r >> 3) * (nch * 128) + ch * 128 + (r & 7) * 16);
+      dst_off[it] = (uint32_t)((cw * 2) * L.x_tile_bytes + (row >> 3) * (nch * 128) + ch * 128 + (row & 7) * 16);
     }
     const uint32_t xbuf_bytes = (uint32_t)(TL_NT * 2 * L.x_tile_bytes);
     for (int t = 0; t < d.T; ++t) {
@@ -349,12 +369,55 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       }
       __syncwarp();
     }
+  } else if (warp >= W_HOP0) {
+    // =========================== hop: D1 (rank rows) -> fp16 hi/lo B operand of stage 2 ============================
+    // warp 16 reads lanes 0..31 (the U1 ranks), warp 17 lanes 32..63 (the W1 ranks in 32..47; the rest has no k)
+    const int quad = warp - W_HOP0;                    // == warp & 3: the TMEM lane quadrant this warp may access
+    const int k = quad * 32 + lane;                    // rank row of D1 = k index of the stage-2 operand
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    tc_fence_before();
+    __syncthreads();                                   // 2^-S1 is in shared memory
+    const float unscale1 = red_s[48];
+    unsigned char* sop0 = k < TL_K2 ? sm + L.s_op + (k >> 3) * ((TL_NS >> 3) * 128) + (k & 7) * 16 : nullptr;
+    for (int t = 0; t < d.T; ++t) {
+#pragma unroll
+      for (int s = 0; s < TL_NT; ++s) {
+        mbar_wait(bar(B_D1FULL + s), t & 1);
+        tc_fence_after();
+        if (quad == 0) TL_TRACE(t, s, 4);
+        const uint32_t d1 = tmem + lane_base + TLM_ACC + s * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float vx[16], vy[16];
+          tmem_ld16(d1 + half * 16, vx);
+          tmem_ld16(d1 + TL_NS + half * 16, vy);
+          tmem_ld_wait();
+          if (sop0) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                split2(vx[g * 8 + 2 * q] + vy[g * 8 + 2 * q], vx[g * 8 + 2 * q + 1] + vy[g * 8 + 2 * q + 1], unscale1, hi[q], lo[q]);
+              unsigned char* dst = sop0 + s * (2 * TL_S_TILE) + (half * 2 + g) * 128;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dst + TL_S_TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_SREADY + s));
+        if (quad == 0) TL_TRACE(t, s, 5);
+      }
+    }
   } else {
     // =========================== epilogue warps ===================================================
     const int ew = warp;                               // 0..15
     const int quad = ew & 3;                           // TMEM lane quadrant
-    const int es = (ew >> 2) & 1;                      // sub-tile
-    const int m = ew >> 3;                             // unit tile (and, for the hop, the row half)
+    const int m = (ew >> 2) & 1;                       // unit tile
+    const int rh = ew >> 3;                            // row half of each sub-tile
     const int part = ew >> 2;                          // 0..3: share of the weight upload
     const int ln = quad * 32 + lane;                   // TMEM lane
     const int gu = m * 128 + ln;                       // hidden unit of this thread
@@ -368,7 +431,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       for (int i = et; i < I * rW; i += nthr) m1 = fmaxf(m1, fabsf(__ldg(a.W1c + i)));
       for (int i = et; i < rW * TL_H; i += nthr) m2 = fmaxf(m2, fabsf(__ldg(a.W2c + i)));
     }
-    float bd = es == 0 ? fabsf(__ldg(a.bias_gate + gu) - __ldg(a.bias_update + gu)) : 0.f;
+    float bd = rh == 0 ? fabsf(__ldg(a.bias_gate + gu) - __ldg(a.bias_update + gu)) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
@@ -384,8 +447,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     if (m1 > 0.f) S1 = min(S1, (int)floorf(log2f(30000.f / m1)));
     if (m2 > 0.f) S2 = min(S2, (int)floorf(log2f(30000.f / m2)));
     S1 = max(S1, -14); S2 = max(S2, -14);
-    const float scale1 = exp2f((float)S1), unscale1 = exp2f((float)-S1);
+    const float scale1 = exp2f((float)S1);
     const float scale2 = exp2f((float)S2), unscale2 = exp2f((float)-S2);
+    if (tid == 0) red_s[48] = exp2f((float)-S1);
 
     // ---- stage-1 weights -> tensor memory.  A1[lane = rank row][k]: lanes 0..31 = U1^T (k = hidden unit), lanes
     //      32..47 = W1^T (k = input feature, its own columns), everything else zero (block diagonal).
@@ -455,43 +519,41 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       kc.tmin = (30.0f - cg) / kS;
     }
 
-    // ---- state: h[row][gu] for the 32 rows of this sub-tile; h_{-1} operand tile
-    float2 hst[TL_NS / 2];
-    unsigned char* hop = sm + L.h_op + es * (2 * TL_H_TILE) + (gu >> 3) * ((TL_NS >> 3) * 128) + (gu & 7) * 16;
-    const int first_row = row0 + es * TL_NS;
+    // ---- state: h[row][gu] for rows [rh*16, rh*16 + 16) of both sub-tiles; h_{-1} operand tiles
+    float2 hst[TL_NT][TL_RPT / 2];
+    unsigned char* hop = sm + L.h_op + (gu >> 3) * ((TL_NS >> 3) * 128) + (rh * 2) * 128 + (gu & 7) * 16;
+    const int first_row = row0 + rh * TL_RPT;          // of sub-tile 0; sub-tile 1: + TL_NS
 #pragma unroll
-    for (int g = 0; g < TL_NS / 8; ++g) {
-      uint32_t hi[4], lo[4];
+    for (int s = 0; s < TL_NT; ++s) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = first_row + g * 8 + 2 * q;
-        const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TL_H + gu) : 0.f;
-        const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TL_H + gu) : 0.f;
-        hst[g * 4 + q] = make_float2(v0, v1);
-        split2(v0, v1, 1.0f, hi[q], lo[q]);
+      for (int g = 0; g < TL_RPT / 8; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = first_row + s * TL_NS + g * 8 + 2 * q;
+          const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TL_H + gu) : 0.f;
+          const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TL_H + gu) : 0.f;
+          hst[s][g * 4 + q] = make_float2(v0, v1);
+          split2(v0, v1, 1.0f, hi[q], lo[q]);
+        }
+        *reinterpret_cast<uint4*>(hop + s * (2 * TL_H_TILE) + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(hop + s * (2 * TL_H_TILE) + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      *reinterpret_cast<uint4*>(hop + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(hop + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();                                   // matches the other roles' prologue barrier
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar(B_HREADY + es));    // phase 0: h_{-1} ready
+    if (lane == 0) { mbar_arrive(bar(B_HREADY)); mbar_arrive(bar(B_HREADY + 1)); }    // phase 0: h_{-1} ready
 
     TlEpiCtx cx;
-    cx.bar_d1full = bar(B_D1FULL + es); cx.bar_sready = bar(B_SREADY + es);
-    cx.bar_dfull = bar(B_DFULL + es); cx.bar_hready = bar(B_HREADY + es);
-    cx.hopper = quad < 2;
-    cx.d1 = tmem + lane_base + TLM_ACC + es * 64 + m * 16;
-    cx.d2 = tmem + lane_base + TLM_ACC + es * 64 + m * TL_NS;
-    cx.sop = nullptr;
-    if (quad < 2 && ln < TL_K2)                          // rank row ln of D1 = k index ln of the stage-2 operand; rows m*16 ..
-      cx.sop = sm + L.s_op + es * (2 * TL_S_TILE) + (ln >> 3) * ((TL_NS >> 3) * 128) + (m * 2) * 128 + (ln & 7) * 16;
+    cx.bar_dfull = bar(B_DFULL); cx.bar_hready = bar(B_HREADY);
+    cx.d2 = tmem + lane_base + TLM_ACC + m * TL_NS + rh * TL_RPT;
     cx.hop = hop;
     cx.out = a.out ? a.out + (size_t)first_row * a.osb + gu : nullptr;
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost;
-    cx.rows_left = d.B - first_row; cx.T = d.T; cx.unscale1 = unscale1;
+    cx.rows_left = d.B - first_row; cx.T = d.T;
+    cx.tr = ew == 0 ? 1 : (ew == 15 ? 2 : 0);
     const bool masked = row0 + TL_ROWS > d.B;
     const int variant = (one_ex2 ? 4 : 0) | (a.out ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
@@ -506,9 +568,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     }
     if (a.h_last) {
 #pragma unroll
-      for (int j = 0; j < TL_NS; ++j) {
-        const int row = first_row + j;
-        if (row < d.B) a.h_last[(size_t)row * TL_H + gu] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
+      for (int s = 0; s < TL_NT; ++s) {
+#pragma unroll
+        for (int j = 0; j < TL_RPT; ++j) {
+          const int row = first_row + s * TL_NS + j;
+          if (row < d.B) a.h_last[(size_t)row * TL_H + gu] = (j & 1) ? hst[s][j >> 1].y : hst[s][j >> 1].x;
+        }
       }
     }
   }
@@ -544,3 +609,9 @@ int launch_tc_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace fgrnn
+
+#ifdef FGRNN_TL_TRACE
+extern "C" __attribute__((visibility("default"))) int fgrnn_debug_tl_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, fgrnn::g_tl_trace, sizeof(long long) * 8 * 2 * 16) == cudaSuccess ? 0 : 6;
+}
+#endif
