@@ -22,7 +22,7 @@ void set_error_detail(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR"};
+static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR", "FGRNN_TC_ALT", "FGRNN_TC_ACC2"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::once_flag g_tune_once;
 static int tune_parse(int key, const char* e) {

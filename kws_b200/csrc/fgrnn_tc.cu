@@ -101,16 +101,29 @@ struct TcSmemLayout {
 // would not fill the SMs otherwise: the per-step chain of a 16-row sub-tile is ~30 % shorter).
 // TC_NT = sub-tiles per CTA: 2 (one set of three MMA warps alternating between them) or 4 (two sets of two MMA
 // warps, each set alternating between its own pair of sub-tiles; 16-row sub-tiles only: 4 x 4 x 16 accumulator columns).
-template <int TC_NS, int TC_NT>
+// ALT (two 32-row sub-tiles only): all sixteen epilogue warps serve BOTH sub-tiles in turn (thread = hidden unit x 8 rows of
+// each sub-tile) instead of eight warps per sub-tile.  The per-step chain of a sub-tile is MMA burst + epilogue; with ALT a
+// sub-tile's epilogue has four warps per scheduler behind it instead of two and takes half the time, and the two sub-tiles
+// alternate strictly (the epilogue warps work on one while the tensor core works on the other).  Same arithmetic per
+// element, same accumulators: results are bit-identical to the non-ALT kernel.
+// ACC2 (two sub-tiles only): TWO accumulators per sub-tile instead of four.  X takes every lo product FIRST and then the
+// hi.hi products of x.W and of h.U k-steps 0..2; Y takes the hi.hi products of h.U k-steps 3..7.  The tensor core truncates
+// each addend of an accumulate at 2^-25 of the largest one, so lo products that enter an accumulator while it is still
+// small lose nothing: the emulator (tools/emulate_tc_schemes.py lofirst2) puts this order at 0.55-0.63 of the tolerance, the
+// same as the four-accumulator scheme (0.54-0.62) -- and the epilogue reads half as much tensor memory per element
+// (tcgen05.ld of four accumulators was the largest single cost of the epilogue).
+template <int TC_NS, int TC_NT, bool ALT = false, bool ACC2 = false>
 struct TcFwd {
+static_assert(!ACC2 || TC_NT == 2, "ACC2: two sub-tiles");
 static_assert(TC_NT == 2 || (TC_NT == 4 && TC_NS == 16), "sub-tile configuration");
-static constexpr int TC_MMA_ROLES = TC_NT == 2 ? 3 : TC_NT4_ROLES;       // warps sharing the 30 MMAs of a sub-tile step
+static_assert(!ALT || (TC_NT == 2 && TC_NS == 32), "ALT: two 32-row sub-tiles");
+static constexpr int TC_MMA_ROLES = ACC2 ? 2 : (TC_NT == 2 ? 3 : TC_NT4_ROLES);       // warps sharing the 30 MMAs of a sub-tile step
 static constexpr int TC_SPS = TC_NT == 2 ? 2 : TC_NT4_SPS;     // sub-tiles served by one set of MMA warps
 static constexpr int TC_MMA_SETS = TC_NT / TC_SPS;
 static constexpr int TC_MMA_WARPS = TC_MMA_ROLES * TC_MMA_SETS;
 static constexpr int TC_THREADS = 32 * (TC_MMA_WARPS + TC_CONV_WARPS + TC_EPI_WARPS);   // 736 or 768
 static constexpr int TC_ROWS = TC_NS * TC_NT;          // batch rows per CTA (64 or 32)
-static constexpr int TC_RH = TC_EPI_WARPS / TC_NT / 4; // row halves per sub-tile (epilogue warps per lane quadrant)
+static constexpr int TC_RH = ALT ? TC_EPI_WARPS / 4 : TC_EPI_WARPS / TC_NT / 4;   // row parts per sub-tile (epilogue warps per lane quadrant)
 static constexpr int TC_CONV_ROWS = TC_ROWS / TC_CONV_WARPS;   // rows per converter warp / TMA box
 static constexpr int TM_ACC_PER_TILE = 4 * TC_NS;      // CA | CB | M1 | M2
 static constexpr int RPT = TC_NS / TC_RH;              // rows per epilogue thread
@@ -248,14 +261,16 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
       float va[8], vb[8], v1[8], v2[8];
       tmem_ld8(cx.acc + g * 8, va);
       tmem_ld8(cx.acc + TC_NS + g * 8, vb);
-      tmem_ld8(cx.acc + 2 * TC_NS + g * 8, v1);
-      tmem_ld8(cx.acc + 3 * TC_NS + g * 8, v2);
+      if (!ACC2) {
+        tmem_ld8(cx.acc + 2 * TC_NS + g * 8, v1);
+        tmem_ld8(cx.acc + 3 * TC_NS + g * 8, v2);
+      }
       tmem_ld_wait();
       if (cx.trace && g == 0) TC_TRACE(t, cx.s, 2);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));
-        const float2 tot = __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
+        const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));     // ACC2: X + Y
+        const float2 tot = ACC2 ? corr : __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
         float2 z, c;
 #ifdef TC_EXP_NO_MATH
         hst[g * 4 + q] = tot; z = tot; c = tot;
@@ -296,6 +311,63 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
   }
 }
 
+// ALT: the same step for rows [rh*8, rh*8 + 8) of sub-tile 0, then of sub-tile 1.  cx describes sub-tile 0; sub-tile 1 is at
+// fixed offsets (barriers + 8 bytes, accumulators + TM_ACC_PER_TILE, operand tiles + 2 * NS * H * 2, rows + NS).
+template <bool HAS_OUT, bool SAVE, bool MASKED, bool ONE_EX2>
+static __device__ __forceinline__ void epilogue_loop_alt(const EpiCtx& cx, const EpiConst& kc, float2 (&hst)[TC_NT][PAIRS]) {
+  static_assert(NG == 1, "ALT: one 8-row group per sub-tile and thread");
+  char* outp = reinterpret_cast<char*>(cx.out);
+  float* zp = cx.zs; float* cp = cx.cs;
+  const uint32_t row_bytes = cx.out_row * 4u;
+  for (int t = 0; t < cx.T; ++t) {
+#pragma unroll
+    for (int s = 0; s < TC_NT; ++s) {
+      TC_CRIT_WAIT(cx.bar_dfull + 8 * s, t & 1);
+      tc_fence_after();
+      float va[8], vb[8], v1[8], v2[8];
+      const uint32_t acc = cx.acc + s * TM_ACC_PER_TILE;
+      tmem_ld8(acc, va);
+      tmem_ld8(acc + TC_NS, vb);
+      if (!ACC2) {
+        tmem_ld8(acc + 2 * TC_NS, v1);
+        tmem_ld8(acc + 3 * TC_NS, v2);
+      }
+      tmem_ld_wait();
+      uint32_t hi[PAIRS], lo[PAIRS];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));     // ACC2: X + Y
+        const float2 tot = ACC2 ? corr : __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
+        float2 z, c;
+        hst[s][q] = gate_update2<ONE_EX2>(tot, hst[s][q], kc, z, c);
+        split_pair(hst[s][q], hi[q], lo[q]);
+        if (SAVE) {
+          const int rj = s * TC_NS + 2 * q;
+          if (!MASKED || rj < cx.rows_left) { zp[rj * TC_H] = z.x; cp[rj * TC_H] = c.x; }
+          if (!MASKED || rj + 1 < cx.rows_left) { zp[(rj + 1) * TC_H] = z.y; cp[(rj + 1) * TC_H] = c.y; }
+        }
+      }
+      unsigned char* hop = cx.hop + s * (2 * TC_NS * TC_H * 2);
+      *reinterpret_cast<uint4*>(hop) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(hop + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + 8 * s);
+      if (HAS_OUT) {
+        char* o = outp + (size_t)(s * TC_NS) * row_bytes;
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+          if (!MASKED || s * TC_NS + 2 * q < cx.rows_left) *reinterpret_cast<float*>(o + (size_t)(2 * q) * row_bytes) = hst[s][q].x;
+          if (!MASKED || s * TC_NS + 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(o + (size_t)(2 * q + 1) * row_bytes) = hst[s][q].y;
+        }
+      }
+    }
+    if (HAS_OUT) outp += (size_t)cx.out_step * 4u;
+    if (SAVE) { zp += cx.zc_step; cp += cx.zc_step; }
+  }
+}
+
 // The 30 MMAs of one sub-tile step (K = 128 of h.U, K = 16*NKX of x.W, three fp16 products each), fully
 // unrolled, split over three issuing warps so that the serial issue latency is a third:
 //   role 0 -> CA : lo terms of x.W (W_lo.x_hi, W_hi.x_lo) and of h.U k-steps 0..2 (U_lo.h_hi, U_hi.h_lo)
@@ -305,6 +377,28 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
 // Every TMEM column and descriptor offset is a compile-time constant on top of uniform bases.
 template <int ROLE, int NKX, bool X_HAS_LO>
 static __device__ __forceinline__ void issue_subtile_mmas(uint32_t tmem, uint32_t acc, uint64_t dXhi, uint64_t dXlo, uint64_t dHhi, uint64_t dHlo) {
+  if (ROLE == 6) {          // ACC2, accumulator X: every lo product first, then hi.hi of x.W and of h.U k-steps 0..2
+#pragma unroll
+    for (int ks = 0; ks < NKX; ++ks) {
+      umma_ts1(acc, tmem + TM_W_LO + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, ks > 0);
+      if (X_HAS_LO) umma_ts1(acc, tmem + TM_W_HI + ks * 8, dXlo + ks * TC_X_KSTEP, TC_IDESC_X, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < TC_H / 16; ++ks) {
+      umma_ts1(acc, tmem + TM_U_LO + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+      umma_ts1(acc, tmem + TM_U_HI + ks * 8, dHlo + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc, tmem + TM_W_HI + ks * 8, dXhi + ks * TC_X_KSTEP, TC_IDESC_X, 1);
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) umma_ts1(acc, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, 1);
+    return;
+  }
+  if (ROLE == 7) {          // ACC2, accumulator Y: hi.hi of h.U k-steps 3..7
+#pragma unroll
+    for (int ks = 3; ks < TC_H / 16; ++ks) umma_ts1(acc + TC_NS, tmem + TM_U_HI + ks * 8, dHhi + ks * TC_H_KSTEP, TC_IDESC_H, ks > 3);
+    return;
+  }
   if (ROLE == 0 || ROLE == 3 || ROLE == 5) {
 #pragma unroll
     for (int ks = 0; ks < NKX; ++ks) {
@@ -376,7 +470,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   constexpr int W_CONV0 = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + TC_CONV_WARPS;
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), TC_TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), TC_EPI_WARPS / TC_NT); mbar_init(bar(B_DFULL + s), TC_MMA_ROLES); }
+    for (int s = 0; s < TC_NT; ++s) { mbar_init(bar(B_HREADY + s), ALT ? TC_EPI_WARPS : TC_EPI_WARPS / TC_NT); mbar_init(bar(B_DFULL + s), TC_MMA_ROLES); }
     for (int b = 0; b < TC_XBUF; ++b) { mbar_init(bar(B_XFULL + b), TC_CONV_WARPS); mbar_init(bar(B_XEMPTY + b), TC_MMA_WARPS); }
     for (int st = 0; st < TC_CONV_WARPS * TC_RAW_STAGES; ++st) mbar_init(bar(B_RAWFULL + st), 1);
     fence_mbar_init();
@@ -435,7 +529,10 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
         tc_mark(20);
         if (leader) {
           tc_mark(21);
-          if (TC_MMA_ROLES == 3) {
+          if (ACC2) {
+            if (role == 0) issue_subtile_dispatch<6>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+            else issue_subtile_dispatch<7>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
+          } else if (TC_MMA_ROLES == 3) {
             if (role == 0) issue_subtile_dispatch<0>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
             else if (role == 1) issue_subtile_dispatch<1>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
             else issue_subtile_dispatch<2>(variant, tmem, acc, dXhi, dXlo, dHhi, dHlo);
@@ -547,8 +644,8 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     // =========================== epilogue warps ===================================================
     const int ew = warp;                               // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access (= ew & 3)
-    const int es = (ew >> 2) % TC_NT;                  // the sub-tile this warp serves
-    const int rh = (ew >> 2) / TC_NT;                  // which part of the sub-tile's rows
+    const int es = ALT ? 0 : (ew >> 2) % TC_NT;        // the sub-tile this warp serves (ALT: both, described from sub-tile 0)
+    const int rh = ALT ? (ew >> 2) : (ew >> 2) / TC_NT; // which part of the sub-tile's rows
     const int n = quad * 32 + lane;                    // hidden unit = TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
@@ -636,6 +733,70 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
       kc.tmin = (30.0f - cg) / kS;
     }
 
+    if constexpr (ALT) {
+      // state: h[row][n] for rows [rh*8, rh*8 + 8) of BOTH sub-tiles
+      float2 hst[TC_NT][PAIRS];
+      unsigned char* hop = sm + L.h_op + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * NG) * 128 + (n & 7) * 16;
+      const int first_row = row0 + rh * RPT;           // of sub-tile 0; sub-tile 1: + TC_NS
+#pragma unroll
+      for (int s = 0; s < TC_NT; ++s) {
+        uint32_t hi[PAIRS], lo[PAIRS];
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+          const int row = first_row + s * TC_NS + 2 * q;
+          const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
+          const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
+          hst[s][q] = make_float2(v0, v1);
+          split2(v0, v1, 1.0f, hi[q], lo[q]);
+        }
+        *reinterpret_cast<uint4*>(hop + s * (2 * TC_NS * TC_H * 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(hop + s * (2 * TC_NS * TC_H * 2) + TC_NS * TC_H * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();                                 // matches the other roles' prologue barrier
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(B_HREADY)); mbar_arrive(bar(B_HREADY + 1)); }    // phase 0: h_{-1} ready
+      EpiCtx cx;
+      cx.bar_dfull = bar(B_DFULL); cx.bar_hready = bar(B_HREADY);
+      cx.acc = tmem + lane_base + TM_ACC + rh * RPT;
+      cx.hop = hop;
+      cx.out = a.out ? a.out + (size_t)first_row * a.osb + n : nullptr;
+      cx.zs = a.save_z ? a.save_z + (size_t)first_row * TC_H + n : nullptr;
+      cx.cs = a.save_c ? a.save_c + (size_t)first_row * TC_H + n : nullptr;
+      cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
+      cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = false; cx.s = 0;
+      const bool masked = row0 + TC_ROWS > d.B;
+      const int variant = (one_ex2 ? 8 : 0) | (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
+      switch (variant) {
+        case 0: epilogue_loop_alt<false, false, false, false>(cx, kc, hst); break;
+        case 1: epilogue_loop_alt<false, false, true, false>(cx, kc, hst); break;
+        case 2: epilogue_loop_alt<false, true, false, false>(cx, kc, hst); break;
+        case 3: epilogue_loop_alt<false, true, true, false>(cx, kc, hst); break;
+        case 4: epilogue_loop_alt<true, false, false, false>(cx, kc, hst); break;
+        case 5: epilogue_loop_alt<true, false, true, false>(cx, kc, hst); break;
+        case 6: epilogue_loop_alt<true, true, false, false>(cx, kc, hst); break;
+        case 7: epilogue_loop_alt<true, true, true, false>(cx, kc, hst); break;
+        case 8: epilogue_loop_alt<false, false, false, true>(cx, kc, hst); break;
+        case 9: epilogue_loop_alt<false, false, true, true>(cx, kc, hst); break;
+        case 10: epilogue_loop_alt<false, true, false, true>(cx, kc, hst); break;
+        case 11: epilogue_loop_alt<false, true, true, true>(cx, kc, hst); break;
+        case 12: epilogue_loop_alt<true, false, false, true>(cx, kc, hst); break;
+        case 13: epilogue_loop_alt<true, false, true, true>(cx, kc, hst); break;
+        case 14: epilogue_loop_alt<true, true, false, true>(cx, kc, hst); break;
+        default: epilogue_loop_alt<true, true, true, true>(cx, kc, hst); break;
+      }
+      if (a.h_last) {
+#pragma unroll
+        for (int s = 0; s < TC_NT; ++s) {
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) {
+            const int row = first_row + s * TC_NS + j;
+            if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[s][j >> 1].y : hst[s][j >> 1].x;
+          }
+        }
+      }
+    } else {
     // state: this thread owns h[row][n] for 16 rows of its sub-tile, kept as row pairs for the fp32x2 pipe
     float2 hst[PAIRS];
     unsigned char* hop = sm + L.h_op + es * (2 * TC_NS * TC_H * 2) + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * NG) * 128 + (n & 7) * 16;
@@ -700,6 +861,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
         if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
       }
     }
+    }   // !ALT
   }
   tc_fence_before();
   __syncthreads();
@@ -708,9 +870,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
 
 };   // struct TcFwd
 
-template <int NS, int NT>
-__global__ void __launch_bounds__((TcFwd<NS, NT>::TC_THREADS), 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
-  TcFwd<NS, NT>::run(ta, xmap);
+template <int NS, int NT, bool ALT = false, bool ACC2 = false>
+__global__ void __launch_bounds__((TcFwd<NS, NT, ALT, ACC2>::TC_THREADS), 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
+  TcFwd<NS, NT, ALT, ACC2>::run(ta, xmap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -735,9 +897,9 @@ bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, in
   return xsb > 0 && xst > 0;
 }
 
-template <int NS, int NT>
+template <int NS, int NT, bool ALT = false, bool ACC2 = false>
 static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
-  using K = TcFwd<NS, NT>;
+  using K = TcFwd<NS, NT, ALT, ACC2>;
   const Dims& d = a.d;
   TcArgs ta{};
   ta.f = a;
@@ -747,9 +909,9 @@ static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
   const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, K::TC_CONV_ROWS, &ta.x_time_outer);
   if (rc) return rc;
   const TcSmemLayout L = K::tc_smem_layout(d.I, ta.KI, esz);
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS, NT, ALT, ACC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const unsigned grid = (unsigned)((d.B + K::TC_ROWS - 1) / K::TC_ROWS);
-  tc_fwd_kernel<NS, NT><<<grid, K::TC_THREADS, L.total, stream>>>(ta, map);
+  tc_fwd_kernel<NS, NT, ALT, ACC2><<<grid, K::TC_THREADS, L.total, stream>>>(ta, map);
   FGRNN_LAUNCH_CHECK("tc_fwd_kernel");
   return FGRNN_OK;
 }
@@ -768,7 +930,15 @@ int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   if (tuning(TUNE_TC_NS) == 32) ns = 32; else if (tuning(TUNE_TC_NS) == 16) ns = 16;
   if (nt == 4) ns = 16;
   if (nt == 4) return launch_tc_fwd_ns<16, 4>(a, stream);
-  return ns == 16 ? launch_tc_fwd_ns<16, 2>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);
+  // Measured on C2 / C5 (round 2, same box, A/B): two accumulators per sub-tile with the lo products first (ACC2) 0.1527 ->
+  // 0.1512 ms / 1.390 -> 1.364 ms, the default for 32-row sub-tiles (FGRNN_TC_ACC2=0 restores four accumulators; 16-row
+  // sub-tiles keep four unless FGRNN_TC_ACC2=1: the training forward at 2048 rows was 2 % slower with two).  Sixteen
+  // epilogue warps alternating between the sub-tiles (FGRNN_TC_ALT=1) is bit-identical but 3-5 % slower: opt-in only.
+  const int t_acc2 = tuning(TUNE_TC_ACC2);
+  const bool acc2 = ns == 16 ? t_acc2 == 1 : t_acc2 != 0, alt = tuning(TUNE_TC_ALT) == 1;
+  if (ns == 16) return acc2 ? launch_tc_fwd_ns<16, 2, false, true>(a, stream) : launch_tc_fwd_ns<16, 2>(a, stream);
+  if (acc2) return alt ? launch_tc_fwd_ns<32, 2, true, true>(a, stream) : launch_tc_fwd_ns<32, 2, false, true>(a, stream);
+  return alt ? launch_tc_fwd_ns<32, 2, true>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);
 }
 
 }  // namespace fgrnn

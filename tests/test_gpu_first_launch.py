@@ -16,6 +16,7 @@ CONFIGS = {
     "ns32_nt2": (dict(FGRNN_TC_NS="32", FGRNN_TC_NT="2"), 1024, 0, 2),
     "ns16_nt4": (dict(FGRNN_TC_NT="4"), 1024, 0, 3),
     "ns32_nt2_save": (dict(FGRNN_TC_NS="32", FGRNN_TC_NT="2"), 200, 1, 4),
+    "ns32_nt2_split_epilogue": (dict(FGRNN_TC_NS="32", FGRNN_TC_NT="2", FGRNN_TC_ALT="0"), 1024, 0, 5),
 }
 
 
@@ -23,7 +24,7 @@ CONFIGS = {
 def test_first_launch_and_poisoned_launches_are_bit_identical(name):
     env_extra, B, save, seed = CONFIGS[name]
     env = dict(os.environ)
-    for k in ("FGRNN_TC_NS", "FGRNN_TC_NT"):
+    for k in ("FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_ALT"):
         env.pop(k, None)
     env.update(env_extra)
     res = subprocess.run([sys.executable, os.path.join(HERE, "first_launch_child.py"), str(B), str(save), str(seed), "24"],

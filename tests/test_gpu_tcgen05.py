@@ -53,18 +53,47 @@ def test_tcgen05_forward_vs_oracle(B, T, I, layout, h0):
     assert torch.equal(last, out[:, -1])
 
 
-@pytest.mark.parametrize("ns,nt", [("16", "2"), ("16", "4"), ("32", "2")])
-def test_tcgen05_forward_every_tile_configuration(tuning, ns, nt):
+@pytest.mark.parametrize("ns,nt,acc2", [("16", "2", None), ("16", "4", None), ("32", "2", None), ("32", "2", "0"), ("16", "2", "1")])
+def test_tcgen05_forward_every_tile_configuration(tuning, ns, nt, acc2):
     """The launcher picks 2x16-row sub-tiles for one-wave batches and 4x16 beyond; FGRNN_TC_NS / FGRNN_TC_NT pin a
     configuration.  All three (incl. the 2x32 variant) must meet the tolerance on ragged, multi-CTA, saved-gate runs."""
     tuning("FGRNN_TC_NS", ns)
     tuning("FGRNN_TC_NT", nt)
+    if acc2 is not None:                               # two accumulators per sub-tile (default for 32-row sub-tiles) or four
+        tuning("FGRNN_TC_ACC2", acc2)
     for (B, T, I, layout, h0, save) in [(77, 9, 32, "HI", True, False), (300, 17, 16, "IH", False, True), (33, 4, 24, "IH", True, False)]:
         out, last, ref, z_s, c_s = _run(B, T, I, layout, h0, seed=21 + B, save=save)
         assert state_ratio(out, ref) <= 1.0, (ns, nt, B)
         assert torch.equal(last, out[:, -1])
         if save:
             assert float(z_s.min()) >= 0.0 and float(z_s.max()) <= 1.0 and float(c_s.abs().max()) <= 1.0
+
+
+def test_tcgen05_alternating_epilogue_is_bit_identical_to_the_split_one(tuning):
+    """2 x 32-row sub-tiles: sixteen epilogue warps serving both sub-tiles in turn (ALT, the default) compute the very
+    bits of the kernel with eight warps per sub-tile (FGRNN_TC_ALT=0) -- states, saved gates, last state; ragged and
+    multi-CTA batches, with and without h0."""
+    from kws_b200 import _lib, engine
+    tuning("FGRNN_TC_NS", "32")
+    tuning("FGRNN_TC_NT", "2")
+    for (B, T, save, h0_given) in [(64, 5, False, False), (77, 9, True, True), (300, 17, True, False), (8192, 6, False, True)]:
+        torch.manual_seed(B)
+        p = O.init_params(32, 128)
+        params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+        x = torch.randn(B, T, 32, device=dev())
+        h0 = 0.5 * torch.randn(B, 128, device=dev()) if h0_given else None
+        kw = dict(layout="IH", batch_first=True, want_last=True, save_for_backward=save, force_path=_lib.PATH_TCGEN05)
+        tuning("FGRNN_TC_ALT", "1")
+        a = engine.forward(x, params, h0, **kw)
+        tuning("FGRNN_TC_ALT", "0")
+        b = engine.forward(x, params, h0, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]), B
+        if save:
+            assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), B
+        if B <= 300:
+            ref = O.unroll(x.cpu(), p, None if h0 is None else h0.cpu().unsqueeze(0), True)
+            assert state_ratio(a[0], ref) <= 1.0
 
 
 def test_tcgen05_time_major_and_saved_gates():

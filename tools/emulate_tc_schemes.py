@@ -71,6 +71,33 @@ def run(seed, scheme, T=99, B=64, h0_given=False, wscale=0.1, SU=8, SW=12, SH=4,
             for k in kh:
                 for (a, b) in ((hl, Uh), (hh, Ul), (hh, Uh)): acc = mma(acc, a[:, k:k+16], b[k:k+16])
             tot = acc.astype(f32)
+        elif scheme == 'lobal2':
+            # two accumulators, each with ITS OWN lo products first: X = x + h k-steps 0..3, Y = h k-steps 4..7
+            X = zero(); Y = zero()
+            for k in kx:
+                for (a, b) in ((xl, Wh), (xh, Wl)): X = mma(X, a[:, k:k+16], b[k:k+16])
+            for k in list(kh)[:4]:
+                for (a, b) in ((hl, Uh), (hh, Ul)): X = mma(X, a[:, k:k+16], b[k:k+16])
+            for k in kx: X = mma(X, xh[:, k:k+16], Wh[k:k+16])
+            for k in list(kh)[:4]: X = mma(X, hh[:, k:k+16], Uh[k:k+16])
+            for k in list(kh)[4:]:
+                for (a, b) in ((hl, Uh), (hh, Ul)): Y = mma(Y, a[:, k:k+16], b[k:k+16])
+            for k in list(kh)[4:]: Y = mma(Y, hh[:, k:k+16], Uh[k:k+16])
+            tot = (X.astype(f32) + Y.astype(f32)).astype(f32)
+        elif scheme.startswith('lofirst'):
+            # G accumulators; accumulator 0 takes ALL lo products first, then its share of the hi.hi chain
+            G = int(scheme[7:])
+            accs = [zero() for _ in range(G)]
+            for k in kx:
+                for (a, b) in ((xl, Wh), (xh, Wl)): accs[0] = mma(accs[0], a[:, k:k+16], b[k:k+16])
+            for k in kh:
+                for (a, b) in ((hl, Uh), (hh, Ul)): accs[0] = mma(accs[0], a[:, k:k+16], b[k:k+16])
+            mains = [(xh, Wh, k) for k in kx] + [(hh, Uh, k) for k in kh]
+            for i, (a, b, k) in enumerate(mains):
+                g = i * G // len(mains)
+                accs[g] = mma(accs[g], a[:, k:k+16], b[k:k+16])
+            tot = accs[G - 1].astype(f32)
+            for g in range(G - 2, -1, -1): tot = (tot + accs[g].astype(f32)).astype(f32)
         else:
             # corrections in their own accumulator
             corr = zero()
