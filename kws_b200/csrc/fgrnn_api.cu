@@ -22,7 +22,7 @@ void set_error_detail(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR", "FGRNN_TC_ALT", "FGRNN_TC_ACC2"};
+static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR", "FGRNN_TC_ALT", "FGRNN_TC_ACC2", "FGRNN_TC_BWD_FUSED"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::once_flag g_tune_once;
 static int tune_parse(int key, const char* e) {
@@ -217,6 +217,8 @@ struct BwdPlan {
   int nchunk, rows_per_chunk, nrec, rows_per_cta;
   bool want_w, want_u;
   bool tc_contract;           // dW / dU sums on the tensor cores (fgrnn_tc_bwd.cu), one partial per CTA
+  int fused_ctas;             // > 0: reverse recurrence + contraction in ONE launch, this many contraction CTAs
+  int* progress;              // [nrec][16] progress flags of the fused launch
   float *UT, *U2T, *U1T;      // workspace copies (nullptr => use caller's pointer directly)
   float *Wf;                  // canonical [I][H] for d_x (nullptr => caller's W usable directly)
   float *dpre, *rec_partial, *partW, *partU, *dWc, *dUc;
@@ -279,6 +281,11 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   pl.want_u = g.d_U || g.d_U1 || g.d_U2;
   pl.tc_contract = tc_contract_ok(g);
   if (pl.tc_contract) pl.nchunk = tc_contract_ctas(dims_of(p));
+  if (pl.tc_contract && pl.path == FGRNN_PATH_TCGEN05 && (pl.want_w || pl.want_u) && tuning(TUNE_TC_BWD_FUSED) != 0) {
+    pl.fused_ctas = tc_bwd_fused_contract_ctas(dims_of(p));
+    if (pl.fused_ctas > 0) pl.nchunk = std::min(pl.fused_ctas, pl.nchunk);
+    pl.fused_ctas = pl.fused_ctas > 0 ? pl.nchunk : 0;
+  }
   Carver cv(ws);
   const bool ih = p.weight_layout == FGRNN_LAYOUT_IH;
   if (ih && pl.path == FGRNN_PATH_GENERIC) {
@@ -288,6 +295,7 @@ BwdPlan plan_backward(const FgrnnBackward& g, void* ws) {
   if (g.d_x && (p.rW > 0 || !ih)) pl.Wf = cv.take<float>((size_t)p.I * p.H);
   pl.dpre = cv.take<float>((size_t)M * p.H);
   pl.rec_partial = cv.take<float>((size_t)pl.nrec * (2 * p.H + 2));
+  if (pl.fused_ctas > 0) pl.progress = cv.take<int>((size_t)pl.nrec * 16);
   if (pl.want_w) pl.partW = cv.take<float>((size_t)pl.nchunk * p.I * p.H);
   if (pl.want_u) pl.partU = cv.take<float>((size_t)pl.nchunk * p.H * p.H);
   if (pl.want_w && p.rW > 0) pl.dWc = cv.take<float>((size_t)p.I * p.H);
@@ -540,6 +548,14 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
     s.hs = g->hs; s.hsb = g->hs_stride_b; s.hst = g->hs_stride_t;
     s.h0 = p.h0; s.z_s = g->z_s; s.c_s = g->c_s;
     s.dpre_ws = pl.dpre; s.rec_partial = pl.rec_partial; s.d_h0 = g->d_h0;
+    if (pl.fused_ctas > 0) {
+      TcContractLaunch c{};
+      c.d = dims_of(p);
+      c.x = p.x; c.xsb = p.x_stride_b; c.xst = p.x_stride_t;
+      c.hs = g->hs; c.hsb = g->hs_stride_b; c.hst = g->hs_stride_t; c.h0 = p.h0;
+      c.dpre = pl.dpre; c.partW = pl.want_w ? pl.partW : nullptr; c.partU = pl.want_u ? pl.partU : nullptr;
+      if ((rc = launch_tc_bwd_fused(s, c, pl.fused_ctas, pl.progress, stream))) return rc;
+    } else
     if ((rc = pl.path == FGRNN_PATH_TCGEN05 ? launch_tc_bwd_rec(s, stream) : launch_smem_bwd_rec(s, stream))) return rc;
   } else {
   BwdRecArgs r{};
@@ -554,7 +570,9 @@ int fgrnn_backward(const FgrnnBackward* g, void* stream_) {
   }
 
   // 3. T-parallel outer-product sums as per-chunk partials (no atomics)
-  if (pl.tc_contract && (pl.want_w || pl.want_u)) {
+  if (pl.fused_ctas > 0) {
+    // done by the fused launch above
+  } else if (pl.tc_contract && (pl.want_w || pl.want_u)) {
     TcContractLaunch c{};
     c.d = dims_of(p);
     c.x = p.x; c.xsb = p.x_stride_b; c.xst = p.x_stride_t;

@@ -143,5 +143,8 @@ int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream);
 bool tc_contract_supports(const Dims& d);
 int tc_contract_ctas(const Dims& d);
 int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream);
+// reverse recurrence and contraction in one launch (the contraction CTAs follow the recurrence on the SMs it leaves free)
+int tc_bwd_fused_contract_ctas(const Dims& d);           // 0: do not fuse
+int launch_tc_bwd_fused(const SmemBwdArgs& a, const TcContractLaunch& c, int ncontract, int* progress, cudaStream_t stream);
 
 }  // namespace fgrnn

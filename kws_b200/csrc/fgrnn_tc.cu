@@ -930,12 +930,12 @@ int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   if (tuning(TUNE_TC_NS) == 32) ns = 32; else if (tuning(TUNE_TC_NS) == 16) ns = 16;
   if (nt == 4) ns = 16;
   if (nt == 4) return launch_tc_fwd_ns<16, 4>(a, stream);
-  // Measured on C2 / C5 (round 2, same box, A/B): two accumulators per sub-tile with the lo products first (ACC2) 0.1527 ->
-  // 0.1512 ms / 1.390 -> 1.364 ms, the default for 32-row sub-tiles (FGRNN_TC_ACC2=0 restores four accumulators; 16-row
-  // sub-tiles keep four unless FGRNN_TC_ACC2=1: the training forward at 2048 rows was 2 % slower with two).  Sixteen
-  // epilogue warps alternating between the sub-tiles (FGRNN_TC_ALT=1) is bit-identical but 3-5 % slower: opt-in only.
-  const int t_acc2 = tuning(TUNE_TC_ACC2);
-  const bool acc2 = ns == 16 ? t_acc2 == 1 : t_acc2 != 0, alt = tuning(TUNE_TC_ALT) == 1;
+  // Measured on C2 / C5 (round 2, same box, A/B): two accumulators per sub-tile with the lo products first (FGRNN_TC_ACC2=1)
+  // 0.1527 -> 0.1512 ms / 1.390 -> 1.364 ms at 32-row sub-tiles, 2 % SLOWER at 16-row sub-tiles (training forward, 2048 rows).
+  // Opt-in: a 1-2 % gain is not worth giving up that every tile configuration computes the very same bits (a 4099-row
+  // shard runs 16-row sub-tiles, the 8192-row batch 32-row ones; tests/test_gpu_fullsize.py compares them bit for bit).
+  // Sixteen epilogue warps alternating between the sub-tiles (FGRNN_TC_ALT=1) is bit-identical but 3-5 % slower: opt-in too.
+  const bool acc2 = tuning(TUNE_TC_ACC2) == 1, alt = tuning(TUNE_TC_ALT) == 1;
   if (ns == 16) return acc2 ? launch_tc_fwd_ns<16, 2, false, true>(a, stream) : launch_tc_fwd_ns<16, 2>(a, stream);
   if (acc2) return alt ? launch_tc_fwd_ns<32, 2, true, true>(a, stream) : launch_tc_fwd_ns<32, 2, false, true>(a, stream);
   return alt ? launch_tc_fwd_ns<32, 2, true>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);

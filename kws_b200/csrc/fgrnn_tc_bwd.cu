@@ -35,6 +35,10 @@ struct TcContractArgs {
   float* partW;                                 // [gridDim.x][I][H]  (null: skip dW)
   float* partU;                                 // [gridDim.x][H][H]  (null: skip dU)
   int nbblk, nchunk;                            // ceil(B/64), T*nbblk
+  // co-running with the reverse recurrence (tc_bwd_fused_kernel): chunks are taken in REVERSE time order and chunk
+  // (t, rows) waits until the recurrence CTAs that own its rows have published T - t finished steps
+  const int* progress;                          // [rec CTAs][16 epilogue warps] finished steps, null = dpre is complete
+  int rec_rows, nrec;                           // rows per recurrence CTA, number of recurrence CTAs
 };
 
 struct CtSmem { int h, d, x, bars, total; int xtile; };
@@ -57,7 +61,7 @@ __device__ __forceinline__ void ct_split8(const float (&v)[8], uint4& hi, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcContractArgs a) {
+static __device__ __forceinline__ void ct_run(const TcContractArgs& a, const int cta, const int ncta) {
   extern __shared__ __align__(128) unsigned char sm[];
   const CtSmem L = ct_smem_layout(a.KI);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);      // [0,1] full, [2,3] empty, [4] done
@@ -73,11 +77,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
     fence_mbar_init();
   }
   tc_fence_before();
-  __syncthreads();
+  asm volatile("bar.sync 2, %0;" ::"n"(CT_THREADS) : "memory");     // the 17 warps of the contraction (the fused kernel has 3 more, exited)
   tc_fence_after();
   if (tmem_base_s != 0u) __trap();               // the CTA owns all 512 columns
   constexpr uint32_t tmem = 0u;
-  const int my_chunks = a.nchunk > (int)blockIdx.x ? (a.nchunk - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_chunks = a.nchunk > cta ? (a.nchunk - 1 - cta) / ncta + 1 : 0;
+  const bool follow = a.progress != nullptr;
 
   if (warp == CT_CONV_WARPS) {
     // =========================== MMA issuer =====================================================
@@ -125,9 +130,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
     constexpr int MAXT = (64 + 8 * 2 + CT_CONV_WARPS - 1) / CT_CONV_WARPS;   // <= 5 tasks per warp
     const int esz = a.x_dtype == FGRNN_BF16 ? 2 : 4;
     for (int j = 0; j < my_chunks; ++j) {
-      const int chunk = (int)blockIdx.x + j * (int)gridDim.x;
+      const int fwd_chunk = cta + j * ncta;
+      const int chunk = follow ? a.nchunk - 1 - fwd_chunk : fwd_chunk;          // following the recurrence: last time step first
       const int t = chunk / a.nbblk, b0 = (chunk - t * a.nbblk) * CT_ROWS;
       const int b = j & 1;
+      if (follow) {
+        // dpre_t of these 64 rows is written by the 16 epilogue warps of 64 / rec_rows recurrence CTAs: one flag per lane
+        const int first = b0 / a.rec_rows, ncta_rows = CT_ROWS / a.rec_rows;
+        const int fl = lane < ncta_rows * 16 ? first * 16 + lane : -1;
+        const int need = a.T - t;                        // published counts are multiples of BR_PUBLISH, or T
+        bool ok = fl < 0 || fl >= a.nrec * 16;
+        for (unsigned spins = 0; !__all_sync(0xffffffffu, ok); ++spins) {
+          if (!ok) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.progress + fl) : "memory");
+            ok = v >= need;
+          }
+          if (spins > (1u << 24)) __trap();              // the recurrence CTAs never wait for anybody: a bug, not a deadlock
+          if (!ok) __nanosleep(200);
+        }
+        __syncwarp();
+      }
       float v[MAXT][8];
 #pragma unroll
       for (int k = 0; k < MAXT; ++k) {
@@ -148,8 +171,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
                 v[k][0] = p0.x; v[k][1] = p0.y; v[k][2] = p0.z; v[k][3] = p0.w; v[k][4] = p1.x; v[k][5] = p1.y; v[k][6] = p1.z; v[k][7] = p1.w;
               }
             } else if (mat == 1) {
+              // dpre may have been written moments ago by a recurrence CTA of the same launch: L2-coherent loads, never the
+              // read-only path
               const float* src = a.dpre + ((size_t)t * a.B + row) * CT_H + col;
-              const float4 p0 = __ldg(reinterpret_cast<const float4*>(src)), p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              const float4 p0 = __ldcg(reinterpret_cast<const float4*>(src)), p1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
               v[k][0] = p0.x; v[k][1] = p0.y; v[k][2] = p0.z; v[k][3] = p0.w; v[k][4] = p1.x; v[k][5] = p1.y; v[k][6] = p1.z; v[k][7] = p1.w;
             } else if (col < a.I && want_w) {
               const int64_t off = (int64_t)row * a.xsb + (int64_t)t * a.xst + col;
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
     const int m = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     if (want_u) {
-      float* dst = a.partU + ((size_t)blockIdx.x * CT_H + m) * CT_H + part * 32;      // row m = k, columns n
+      float* dst = a.partU + ((size_t)cta * CT_H + m) * CT_H + part * 32;      // row m = k, columns n
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float vm[16], vc[16];
@@ -237,13 +262,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcCont
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (c0 + q < a.I) a.partW[((size_t)blockIdx.x * a.I + c0 + q) * CT_H + m] = vm[q] + vc[q];
+          if (c0 + q < a.I) a.partW[((size_t)cta * a.I + c0 + q) * CT_H + m] = vm[q] + vc[q];
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  asm volatile("bar.sync 2, %0;" ::"n"(CT_THREADS) : "memory");     // the 17 warps of the contraction (the fused kernel has 3 more, exited)
   if (warp == CT_CONV_WARPS) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1) tc_contract_kernel(const TcContractArgs a) {
+  ct_run(a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,6 +317,7 @@ int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream) {
 // live in per-thread registers for the whole kernel and leave as one partial row per CTA.
 // =============================================================================================
 constexpr int BR_H = 128, BR_NT = 2;
+constexpr int BR_PUBLISH = 8;                   // fused launch: steps between two progress reports to the contraction CTAs
 constexpr int BR_EPI_WARPS = 16, BR_MMA_WARPS = 3;
 constexpr int BR_W_PROD = BR_EPI_WARPS, BR_W_MMA = BR_EPI_WARPS + 1;
 constexpr int BR_THREADS = 32 * (BR_EPI_WARPS + 1 + BR_MMA_WARPS);      // 640
@@ -322,7 +352,7 @@ static __host__ __device__ inline BrSmem br_smem_layout() {
   return L;
 }
 
-static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& maps, const int g_time_outer, const int hs_time_outer) {
+static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& maps, const int g_time_outer, const int hs_time_outer, int* progress = nullptr) {
   extern __shared__ __align__(128) unsigned char sm[];
   const BrSmem L = br_smem_layout();
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
@@ -551,6 +581,14 @@ static __device__ __forceinline__ void run(const SmemBwdArgs& a, const BrMaps& m
         if (2 * q < rows_left) dst[(2 * q) * BR_H] = dp[q].x;
         if (2 * q + 1 < rows_left) dst[(2 * q + 1) * BR_H] = dp[q].y;
       }
+      if (progress && (((it + 1) & (BR_PUBLISH - 1)) == 0 || it == d.T - 1)) {
+        // the contraction CTAs follow this kernel: publish "this warp's part of dpre is in memory up to this step".  A
+        // gpu-scope fence under memory load costs about a microsecond (measured: one per step made the recurrence 70 %
+        // slower), so the progress is published every BR_PUBLISH steps only.
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(progress + blockIdx.x * BR_EPI_WARPS + ew), "r"(it + 1) : "memory");
+      }
     }
 
     // per-CTA partial row: d_bias_gate | d_bias_update | d_zeta (raw) | d_nu (raw); fixed summation order
@@ -588,6 +626,20 @@ __global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_rec_kernel(const SmemBwd
   BrK<NS>::run(a, maps, g_time_outer, hs_time_outer);
 }
 
+// The reverse recurrence keeps one CTA per 32 or 64 batch rows busy (64 of 148 SMs at the data-parallel training batch of
+// 2048 rows) and the contraction needs its dpre_t only step by step: ONE launch runs both, recurrence CTAs first in the
+// grid (they wait for nobody), contraction CTAs on the SMs left over, following the published progress.
+template <int NS>
+__global__ void __launch_bounds__(BR_THREADS, 1) tc_bwd_fused_kernel(const SmemBwdArgs a, const __grid_constant__ BrMaps maps, const int g_time_outer,
+                                                                     const int hs_time_outer, const TcContractArgs c, int* progress) {
+  if ((int)blockIdx.x < c.nrec) {
+    BrK<NS>::run(a, maps, g_time_outer, hs_time_outer, progress);
+  } else {
+    if ((int)(threadIdx.x >> 5) > CT_CONV_WARPS) return;                       // the contraction uses 17 of the 20 warps
+    ct_run(c, (int)blockIdx.x - c.nrec, (int)gridDim.x - c.nrec);
+  }
+}
+
 bool tc_bwd_rec_supports(const Dims& d) {
   return d.rW == 0 && d.rU == 0 && d.H == BR_H && d.gate_nl == FGRNN_NL_SIGMOID && d.update_nl == FGRNN_NL_TANH;
 }
@@ -623,6 +675,51 @@ static int launch_tc_bwd_rec_ns(const SmemBwdArgs& a, cudaStream_t stream) {
 int launch_tc_bwd_rec(const SmemBwdArgs& a, cudaStream_t stream) {
   if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
   return br_ns_for(a.d.B) == 16 ? launch_tc_bwd_rec_ns<16>(a, stream) : launch_tc_bwd_rec_ns<32>(a, stream);
+}
+
+// Contraction CTAs of the fused launch: whatever the recurrence leaves free, 0 = do not fuse (the recurrence fills the GPU,
+// or too few SMs would be left to follow it).
+int tc_bwd_fused_contract_ctas(const Dims& d) {
+  const int left = 148 - tc_bwd_rec_ctas(d);
+  return left >= 48 ? left : 0;
+}
+
+template <int BR_NS>
+static int launch_tc_bwd_fused_ns(const SmemBwdArgs& a, const TcContractLaunch& c, int ncontract, int* progress, cudaStream_t stream) {
+  using K = BrK<BR_NS>;
+  const Dims& d = a.d;
+  BrMaps maps;
+  int g_to = 0, hs_to = 0, dummy = 0, rc;
+  if ((rc = make_row_tile_map(&maps.g, a.grad_h, false, BR_H, d.B, d.T - a.gt0, a.gsb, a.gst, BR_NS, &g_to))) return rc;
+  if ((rc = make_row_tile_map(&maps.z, a.z_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  if ((rc = make_row_tile_map(&maps.c, a.c_s, false, BR_H, d.B, d.T, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  const float* hs = a.hs ? a.hs : a.z_s;
+  if ((rc = make_row_tile_map(&maps.hs, hs, false, BR_H, d.B, d.T, a.hs ? a.hsb : BR_H, a.hs ? a.hst : (int64_t)d.B * BR_H, BR_NS, &hs_to))) return rc;
+  const float* h0 = a.h0 ? a.h0 : a.z_s;
+  if ((rc = make_row_tile_map(&maps.h0, h0, false, BR_H, d.B, 1, BR_H, (int64_t)d.B * BR_H, BR_NS, &dummy))) return rc;
+  TcContractArgs ca{};
+  ca.B = d.B; ca.T = d.T; ca.I = d.I; ca.KI = (d.I + 15) & ~15;
+  ca.x_dtype = d.x_dtype;
+  ca.x = c.x; ca.xsb = c.xsb; ca.xst = c.xst;
+  ca.hs = c.hs; ca.hsb = c.hsb; ca.hst = c.hst; ca.h0 = c.h0; ca.dpre = c.dpre;
+  ca.partW = c.partW; ca.partU = c.partU;
+  ca.nbblk = (d.B + CT_ROWS - 1) / CT_ROWS;
+  ca.nchunk = d.T * ca.nbblk;
+  ca.progress = progress; ca.rec_rows = K::BR_ROWS; ca.nrec = (d.B + K::BR_ROWS - 1) / K::BR_ROWS;
+  const BrSmem L = K::br_smem_layout();
+  const CtSmem CL = ct_smem_layout(ca.KI);
+  const int smem = L.total > CL.total ? L.total : CL.total;
+  FGRNN_CUDA_TRY(cudaMemsetAsync(progress, 0, sizeof(int) * (size_t)ca.nrec * BR_EPI_WARPS, stream));
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_bwd_fused_kernel<BR_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_bwd_fused_kernel<BR_NS><<<ca.nrec + ncontract, BR_THREADS, smem, stream>>>(a, maps, g_to, hs_to, ca, progress);
+  FGRNN_LAUNCH_CHECK("tc_bwd_fused_kernel");
+  return FGRNN_OK;
+}
+
+int launch_tc_bwd_fused(const SmemBwdArgs& a, const TcContractLaunch& c, int ncontract, int* progress, cudaStream_t stream) {
+  if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
+  return br_ns_for(a.d.B) == 16 ? launch_tc_bwd_fused_ns<16>(a, c, ncontract, progress, stream)
+                                : launch_tc_bwd_fused_ns<32>(a, c, ncontract, progress, stream);
 }
 
 }  // namespace fgrnn
