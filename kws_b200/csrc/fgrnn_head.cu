@@ -121,8 +121,16 @@ __global__ void __launch_bounds__(HD_THREADS) head_nll_kernel(const HeadArgs a) 
   __threadfence();
   const int n = C * H + C + 1;
   for (int i = tid; i < n; i += HD_THREADS) {
+    // fixed order (run-to-run identical), sixteen independent loads in flight per thread: a plain `s += partial[g]` loop
+    // serialises the L2 round trips (measured 43 us for the whole kernel at 32 CTAs)
     float s = 0.f;
-    for (unsigned g = 0; g < gridDim.x; ++g) s += a.partial[(size_t)g * n + i];       // fixed order: run-to-run identical
+    for (unsigned g0 = 0; g0 < gridDim.x; g0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = g0 + j < gridDim.x ? __ldcg(a.partial + (size_t)(g0 + j) * n + i) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+    }
     if (i < C * H) a.dW[i] = s;
     else if (i < C * H + C) a.db[i - C * H] = s;
     else a.loss[0] = s;

@@ -113,7 +113,7 @@ def test_fused_step_matches_autograd_on_the_oracle(B, T, batch_first):
         loss_r.backward()
         loss = step.compute(x.to(dev()), labels.to(dev()))
         torch.cuda.synchronize()
-        assert abs(float(loss) - float(loss_r)) <= 1e-5 * abs(float(loss_r)) + 1e-6
+        assert abs(float(loss) - float(loss_r.detach())) <= 1e-5 * abs(float(loss_r.detach())) + 1e-6
         for k, v in ref_params.items():
             assert grad_ratio(getattr(layer.cell, k).grad, v.grad) <= 1.0, (it, k)
         assert grad_ratio(head.weight.grad, head_ref.weight.grad) <= 1.0
