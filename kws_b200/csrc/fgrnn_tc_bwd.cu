@@ -317,7 +317,10 @@ int launch_tc_contract(const TcContractLaunch& c, cudaStream_t stream) {
 // live in per-thread registers for the whole kernel and leave as one partial row per CTA.
 // =============================================================================================
 constexpr int BR_H = 128, BR_NT = 2;
-constexpr int BR_PUBLISH = 8;                   // fused launch: steps between two progress reports to the contraction CTAs
+#ifndef FGRNN_BR_PUBLISH
+#define FGRNN_BR_PUBLISH 8
+#endif
+constexpr int BR_PUBLISH = FGRNN_BR_PUBLISH;                   // fused launch: steps between two progress reports to the contraction CTAs
 constexpr int BR_EPI_WARPS = 16, BR_MMA_WARPS = 3;
 constexpr int BR_W_PROD = BR_EPI_WARPS, BR_W_MMA = BR_EPI_WARPS + 1;
 constexpr int BR_THREADS = 32 * (BR_EPI_WARPS + 1 + BR_MMA_WARPS);      // 640

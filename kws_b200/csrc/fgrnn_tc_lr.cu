@@ -2,21 +2,23 @@
 // H = 256, wRank 16, uRank 32, I = 32):   pre_t = (x_t.W1).W2 + (h_{t-1}.U1).U2   in the reference's factored order
 // (rnn.py:280-287), as two chained tensor-core stages per time step:
 //
-//   stage 1   D1^T[rank][row] = [U1^T ; W1^T] . [h_{t-1} ; x_t]^T     M = 128 (48 used: lanes 0..31 = the U1 ranks,
-//             lanes 32..47 = the W1 ranks; A is block diagonal), K = 256 + KI, N = 32 batch rows
-//   hop       the 48 rank rows leave tensor memory (tcgen05.ld), are un-scaled, split into fp16 hi/lo and written as the
-//             MN-major [48][32] B operand of stage 2 (four of the sub-tile's epilogue warps do this)
+//   stage 1   D1^T[rank row][row] = A1 . [h_{t-1} ; x_t]^T            M = 128, K = 256 + KI, N = 32 batch rows.  The fp16 hi and
+//             lo parts of the weights are STACKED on the M rows (lane quadrant q < 2: lanes 0..15 = U1_hi^T of ranks 16q..16q+15,
+//             lanes 16..31 = U1_lo^T of the same ranks; quadrant 2: W1_hi^T | W1_lo^T; A is block diagonal), so one MMA with
+//             B = h_hi yields hi.hi in the main rows AND U1_lo.h_hi in the correction rows: two MMAs per k-step, not three
+//   hop       three warps (lane quadrants 0..2) read the rank rows (tcgen05.ld), add each main row and its correction row
+//             (one shuffle), un-scale, split into fp16 hi/lo and write the MN-major [48][32] B operand of stage 2
 //   stage 2   D2^T[unit][row] = [U2^T | W2^T] . [s ; sx]              two M = 128 tiles (256 units), K = 48, N = 32
 //   epilogue  gate update (rnn.py:289-295) exactly as fgrnn_tc.cu: thread = hidden unit, 32 rows, h in registers
 //
 // Warp roles (24 warps): 0..15 epilogue -- ALL of them serve both sub-tiles in turn (thread = hidden unit x 16 rows of
 // each sub-tile), so that a sub-tile's epilogue has four warps per scheduler behind it: the per-step chain of a sub-tile
 // (stage 1 -> hop -> stage 2 -> epilogue) is what bounds the kernel, and with eight warps per sub-tile the epilogue alone
-// was half of it (tools/trace_lowrank.py); 16..17 hop (lane quadrants 0 and 1, no global stores in flight when they
-// fence); 18..19 x path (TMA -> fp16 split, one sub-tile each); 20..23 MMA issue ([sub-tile][role]).
+// was half of it (tools/trace_lowrank.py); 16..18 hop (lane quadrants 0..2, no global stores in flight when they
+// fence); 19..20 x path (TMA -> fp16 split, one sub-tile each); 21..24 MMA issue ([sub-tile][role]).
 //
-// Both weight sets stay in TENSOR MEMORY for the whole kernel (fp16 hi/lo pairs): stage 1 takes 288 columns, stage 2
-// 96, which leaves 128 columns = 64 per sub-tile.  D1 and D2 of a sub-tile are never live at the same time (D1 dies when
+// Both weight sets stay in TENSOR MEMORY for the whole kernel: stage 1 takes 144 columns (hi and lo share them, on different
+// lanes), stage 2 96 (fp16 hi | lo).  D1 and D2 of a sub-tile are never live at the same time (D1 dies when
 // the hop has read it, D2 when the epilogue has read it), so they ALIAS: two sub-tiles of 32 rows per CTA run half a
 // period apart, each with its own pair of MMA-issuing warps.
 //
@@ -33,14 +35,14 @@ namespace fgrnn {
 
 constexpr int TL_H = 256, TL_NS = 32, TL_NT = 2, TL_ROWS = TL_NS * TL_NT;
 constexpr int TL_RU = 32, TL_RW = 16, TL_K2 = TL_RU + TL_RW;            // padded ranks; K of stage 2
-constexpr int TL_EPI_WARPS = 16, TL_HOP_WARPS = 2, TL_CONV_WARPS = 2, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
+constexpr int TL_EPI_WARPS = 16, TL_HOP_WARPS = 3, TL_CONV_WARPS = 2, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
 constexpr int TL_THREADS = 32 * (TL_EPI_WARPS + TL_HOP_WARPS + TL_CONV_WARPS + TL_MMA_WARPS);
 constexpr int TL_RPT = TL_NS / 2;                     // rows of each sub-tile per epilogue thread
 constexpr int TL_XBUF = 4, TL_RAW_STAGES = 4, TL_CONV_ROWS = TL_ROWS / TL_CONV_WARPS;
 constexpr int TL_MAX_KI = 32;
 // tensor-memory column map
-constexpr uint32_t TLM_A1_HI = 0, TLM_A1X_HI = 128, TLM_A1_LO = 144, TLM_A1X_LO = 272;     // stage-1 weights: h part | x part
-constexpr uint32_t TLM_A2 = 288;                      // + m * 48 + {0: hi, 24: lo}
+constexpr uint32_t TLM_A1 = 0, TLM_A1X = 128;         // stage-1 weights (hi | lo stacked on the lanes): h part 128 columns, x part 16
+constexpr uint32_t TLM_A2 = 144;                      // + m * 48 + {0: hi, 24: lo}
 constexpr uint32_t TLM_ACC = 384;                     // + s * 64:  D1 = X | Y (32 columns each), aliased by D2 = tile 0 | tile 1
 constexpr int TL_H_TILE = TL_H * TL_NS * 2;           // one fp16 [256][32] operand tile: 16 KB
 constexpr int TL_S_TILE = TL_K2 * TL_NS * 2;          // one fp16 [48][32] operand tile: 3 KB
@@ -180,31 +182,25 @@ static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, cons
   }
 }
 
-// Stage 1 of one sub-tile step, straight-line on the elected lane.  Every accumulator takes its lo products first and its
-// hi.hi products after them (see the header):
-//   role 0 -> X: lo of h k-steps 0..7, lo of x, hi.hi of h k-steps 0..7, hi.hi of x        (the x part lands in lanes 32..47)
-//   role 1 -> Y: lo of h k-steps 8..15, hi.hi of h k-steps 8..15
+// Stage 1 of one sub-tile step, straight-line on the elected lane.  Every accumulator takes its lo products first (B = the
+// lo part of h / x: main rows get W_hi.v_lo) and the hi.hi products after them (B = the hi part: main rows get hi.hi, the
+// correction rows W_lo.v_hi), see the header:
+//   role 0 -> X: h k-steps 0..7 and x                  role 1 -> Y: h k-steps 8..15
 template <int ROLE, int NKX, bool X_HAS_LO>
 static __device__ __forceinline__ void tl_issue_stage1(uint32_t acc, uint64_t dHhi, uint64_t dHlo, uint64_t dXhi, uint64_t dXlo) {
   constexpr uint32_t tmem = 0u;
   constexpr int k0 = ROLE * 8;
 #pragma unroll
-  for (int ks = k0; ks < k0 + 8; ++ks) {
-    umma_ts1(acc, tmem + TLM_A1_LO + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > k0);
-    umma_ts1(acc, tmem + TLM_A1_HI + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
-  }
-  if (ROLE == 0) {
+  for (int ks = k0; ks < k0 + 8; ++ks) umma_ts1(acc, tmem + TLM_A1 + ks * 8, dHlo + ks * TL_MN_KSTEP, TL_IDESC_MN, ks > k0);
+  if (ROLE == 0 && X_HAS_LO) {
 #pragma unroll
-    for (int ks = 0; ks < NKX; ++ks) {
-      umma_ts1(acc, tmem + TLM_A1X_LO + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
-      if (X_HAS_LO) umma_ts1(acc, tmem + TLM_A1X_HI + ks * 8, dXlo + ks * TL_X_KSTEP, TL_IDESC_X, 1);
-    }
+    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc, tmem + TLM_A1X + ks * 8, dXlo + ks * TL_X_KSTEP, TL_IDESC_X, 1);
   }
 #pragma unroll
-  for (int ks = k0; ks < k0 + 8; ++ks) umma_ts1(acc, tmem + TLM_A1_HI + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
+  for (int ks = k0; ks < k0 + 8; ++ks) umma_ts1(acc, tmem + TLM_A1 + ks * 8, dHhi + ks * TL_MN_KSTEP, TL_IDESC_MN, 1);
   if (ROLE == 0) {
 #pragma unroll
-    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc, tmem + TLM_A1X_HI + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
+    for (int ks = 0; ks < NKX; ++ks) umma_ts1(acc, tmem + TLM_A1X + ks * 8, dXhi + ks * TL_X_KSTEP, TL_IDESC_X, 1);
   }
 }
 
@@ -371,14 +367,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     }
   } else if (warp >= W_HOP0) {
     // =========================== hop: D1 (rank rows) -> fp16 hi/lo B operand of stage 2 ============================
-    // warp 16 reads lanes 0..31 (the U1 ranks), warp 17 lanes 32..63 (the W1 ranks in 32..47; the rest has no k)
+    // warp 16 + q reads lane quadrant q: lanes 0..15 = the main rows of 16 ranks, lanes 16..31 = their correction rows
     const int quad = warp - W_HOP0;                    // == warp & 3: the TMEM lane quadrant this warp may access
-    const int k = quad * 32 + lane;                    // rank row of D1 = k index of the stage-2 operand
+    const int k = quad * 16 + (lane & 15);             // k index of the stage-2 operand: U1 ranks 0..31, then W1 ranks
+    const int half_lane = lane >> 4;                   // which 8 of a half's 16 batch rows this lane converts and stores
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     tc_fence_before();
     __syncthreads();                                   // 2^-S1 is in shared memory
     const float unscale1 = red_s[48];
-    unsigned char* sop0 = k < TL_K2 ? sm + L.s_op + (k >> 3) * ((TL_NS >> 3) * 128) + (k & 7) * 16 : nullptr;
+    unsigned char* sop0 = sm + L.s_op + (k >> 3) * ((TL_NS >> 3) * 128) + (k & 7) * 16;
     for (int t = 0; t < d.T; ++t) {
 #pragma unroll
       for (int s = 0; s < TL_NT; ++s) {
@@ -392,18 +389,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
           tmem_ld16(d1 + half * 16, vx);
           tmem_ld16(d1 + TL_NS + half * 16, vy);
           tmem_ld_wait();
-          if (sop0) {
+          float mine[8];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                split2(vx[g * 8 + 2 * q] + vy[g * 8 + 2 * q], vx[g * 8 + 2 * q + 1] + vy[g * 8 + 2 * q + 1], unscale1, hi[q], lo[q]);
-              unsigned char* dst = sop0 + s * (2 * TL_S_TILE) + (half * 2 + g) * 128;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst + TL_S_TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
+          for (int c = 0; c < 16; ++c) {
+            const float v = vx[c] + vy[c];
+            const float tot = v + __shfl_xor_sync(0xffffffffu, v, 16);      // main row + correction row: the same sum on both lanes
+            if (c < 8) mine[c] = tot; else if (half_lane) mine[c - 8] = tot;
           }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split2(mine[2 * q], mine[2 * q + 1], unscale1, hi[q], lo[q]);
+          unsigned char* dst = sop0 + s * (2 * TL_S_TILE) + (half * 2 + half_lane) * 128;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + TL_S_TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -451,32 +449,40 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     const float scale2 = exp2f((float)S2), unscale2 = exp2f((float)-S2);
     if (tid == 0) red_s[48] = exp2f((float)-S1);
 
-    // ---- stage-1 weights -> tensor memory.  A1[lane = rank row][k]: lanes 0..31 = U1^T (k = hidden unit), lanes
-    //      32..47 = W1^T (k = input feature, its own columns), everything else zero (block diagonal).
-    for (int kb = part; kb < 16; kb += 4) {              // h part: 16 k-blocks of 16 units
-      uint32_t hi[8], lo[8];
+    // ---- stage-1 weights -> tensor memory.  A1[lane][k]: quadrant q < 2: lanes 0..15 = the hi part of U1^T for ranks
+    //      16q..16q+15, lanes 16..31 = the lo part of the same ranks (k = hidden unit); quadrant 2: W1^T likewise (k = input
+    //      feature, its own columns); everything else zero (block diagonal).
+    {
+      const int rank = (quad & 1) * 16 + (lane & 15);
+      const bool take_lo = (lane >> 4) != 0;
+      const bool u_row = quad < 2 && rank < rU, w_row = quad == 2 && (lane & 15) < rW;
+      for (int kb = part; kb < 16; kb += 4) {            // h part: 16 k-blocks of 16 units
+        uint32_t sel[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = kb * 16 + 2 * j;
-        const float v0 = (quad == 0 && lane < rU) ? __ldg(a.U1c + (size_t)k * rU + lane) : 0.f;
-        const float v1 = (quad == 0 && lane < rU) ? __ldg(a.U1c + (size_t)(k + 1) * rU + lane) : 0.f;
-        split2(v0, v1, scale1, hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) {
+          const int kk = kb * 16 + 2 * j;
+          const float v0 = u_row ? __ldg(a.U1c + (size_t)kk * rU + rank) : 0.f;
+          const float v1 = u_row ? __ldg(a.U1c + (size_t)(kk + 1) * rU + rank) : 0.f;
+          uint32_t hi, lo;
+          split2(v0, v1, scale1, hi, lo);
+          sel[j] = take_lo ? lo : hi;
+        }
+        tmem_st8(tmem + lane_base + TLM_A1 + kb * 8, sel);
       }
-      tmem_st8(tmem + lane_base + TLM_A1_HI + kb * 8, hi);
-      tmem_st8(tmem + lane_base + TLM_A1_LO + kb * 8, lo);
-    }
-    if (part < 2) {                                      // x part: 2 k-blocks of 16 features
-      const int kb = part;
-      uint32_t hi[8], lo[8];
+      if (part < 2) {                                    // x part: 2 k-blocks of 16 features
+        const int kb = part;
+        uint32_t sel[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = kb * 16 + 2 * j;
-        const float v0 = (quad == 1 && lane < rW && k < I) ? __ldg(a.W1c + (size_t)k * rW + lane) : 0.f;
-        const float v1 = (quad == 1 && lane < rW && k + 1 < I) ? __ldg(a.W1c + (size_t)(k + 1) * rW + lane) : 0.f;
-        split2(v0, v1, scale1, hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) {
+          const int kk = kb * 16 + 2 * j;
+          const float v0 = (w_row && kk < I) ? __ldg(a.W1c + (size_t)kk * rW + (lane & 15)) : 0.f;
+          const float v1 = (w_row && kk + 1 < I) ? __ldg(a.W1c + (size_t)(kk + 1) * rW + (lane & 15)) : 0.f;
+          uint32_t hi, lo;
+          split2(v0, v1, scale1, hi, lo);
+          sel[j] = take_lo ? lo : hi;
+        }
+        tmem_st8(tmem + lane_base + TLM_A1X + kb * 8, sel);
       }
-      tmem_st8(tmem + lane_base + TLM_A1X_HI + kb * 8, hi);
-      tmem_st8(tmem + lane_base + TLM_A1X_LO + kb * 8, lo);
     }
     // ---- stage-2 weights: A2[tile][lane = unit][j]: j < 32 -> U2[j][unit], 32 <= j < 48 -> W2[j - 32][unit]
     {
