@@ -23,85 +23,108 @@ struct HeadArgs {
   float inv_b;
 };
 
+// Every phase keeps several short, independent FMA chains per thread (the first version had one 128- / 64-step chain per
+// thread and phase and took 23 us for a single CTA: latency bound with eight warps per SM).
 __global__ void __launch_bounds__(HD_THREADS) head_nll_kernel(const HeadArgs a) {
   extern __shared__ float hsm[];
-  const int H = a.H, C = a.C, Hp = H + 4;
-  float* Ws = hsm;                                 // [C][H]
-  float* hs = Ws + C * H;                          // [ROWS][Hp]
-  float* dl = hs + HD_ROWS * Hp;                   // [ROWS][HD_MAXC]
+  const int H = a.H, C = a.C, Hp = H + 4;          // padded pitch: rows (and classes) land in different banks
+  float* Ws = hsm;                                 // [C][Hp]
+  float* hs = Ws + C * Hp;                         // [ROWS][Hp]
+  float* dl = hs + HD_ROWS * Hp;                   // [ROWS][HD_MAXC]: logits, then dlogits
   float* red = dl + HD_ROWS * HD_MAXC;             // [ROWS] loss terms
   __shared__ bool last;
   const int tid = threadIdx.x, row0 = blockIdx.x * HD_ROWS;
-  for (int i = tid; i < C * H; i += HD_THREADS) Ws[i] = __ldg(a.W + i);
-  for (int i = tid; i < HD_ROWS * (H / 4); i += HD_THREADS) {
-    const int r = i / (H / 4), c4 = i - r * (H / 4);
-    const float4 v = row0 + r < a.B ? __ldg(reinterpret_cast<const float4*>(a.h + (int64_t)(row0 + r) * a.h_stride) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(hs + r * Hp + c4 * 4) = v;
+  const int H4 = H >> 2;
+  for (int i = tid; i < C * H; i += HD_THREADS) {       // scalar loads: W may sit at any 4-byte offset of a flat parameter buffer
+    const int c = i / H, k = i - c * H;
+    Ws[c * Hp + k] = __ldg(a.W + i);
+  }
+  for (int i = tid; i < HD_ROWS * H4; i += HD_THREADS) {
+    const int r = i / H4, k4 = i - r * H4;
+    const float4 v = row0 + r < a.B ? __ldg(reinterpret_cast<const float4*>(a.h + (int64_t)(row0 + r) * a.h_stride) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(hs + r * Hp + k4 * 4) = v;
   }
   __syncthreads();
-  // logits: 4 threads per row, thread q takes classes q, q+4, q+8, q+12
+  // ---- logits: item = (row, class); up to four items per thread, their chains interleaved
   {
-    const int r = tid >> 2, q = tid & 3;
-    float lg[4];
+    constexpr int NI = (HD_ROWS * HD_MAXC + HD_THREADS - 1) / HD_THREADS;     // 4
+    const int nitem = HD_ROWS * C;
+    const float* hp[NI]; const float* wp[NI]; float acc[NI]; int rr[NI], cc[NI];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = q + 4 * j;
-      float s = -INFINITY;
-      if (c < C) {
-        s = __ldg(a.b + c);
-        const float* w = Ws + c * H; const float* hr = hs + r * Hp;
-        for (int k = 0; k < H; k += 4) {
-          const float4 hv = *reinterpret_cast<const float4*>(hr + k), wv = *reinterpret_cast<const float4*>(w + k);
-          s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s); s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
-        }
-      }
-      lg[j] = s;
+    for (int j = 0; j < NI; ++j) {
+      const int it = tid + j * HD_THREADS, live = it < nitem;
+      rr[j] = live ? it / C : 0; cc[j] = live ? it - rr[j] * C : 0;
+      hp[j] = hs + rr[j] * Hp; wp[j] = Ws + cc[j] * Hp;
+      acc[j] = live ? __ldg(a.b + cc[j]) : 0.f;
     }
-    float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float se = 0.f;
+    for (int k = 0; k < H; k += 4) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) se += (q + 4 * j < C) ? expf(lg[j] - mx) : 0.f;
-    se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
-    const float lse = mx + logf(se);
+      for (int j = 0; j < NI; ++j) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp[j] + k), wv = *reinterpret_cast<const float4*>(wp[j] + k);
+        acc[j] = fmaf(hv.x, wv.x, acc[j]); acc[j] = fmaf(hv.y, wv.y, acc[j]); acc[j] = fmaf(hv.z, wv.z, acc[j]); acc[j] = fmaf(hv.w, wv.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+      if (tid + j * HD_THREADS < nitem) dl[rr[j] * HD_MAXC + cc[j]] = acc[j];
+  }
+  __syncthreads();
+  // ---- log-softmax, loss term and dlogits: one thread per row (C <= 16)
+  if (tid < HD_ROWS) {
+    const int r = tid;
     const bool live = row0 + r < a.B;
     const int lab = live ? (int)a.labels[row0 + r] : -1;
+    float lg[HD_MAXC], mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < HD_MAXC; ++c) { lg[c] = c < C ? dl[r * HD_MAXC + c] : -INFINITY; mx = fmaxf(mx, lg[c]); }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD_MAXC; ++c) se += c < C ? expf(lg[c] - mx) : 0.f;
+    const float lse = mx + logf(se);
     float lt = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = q + 4 * j;
+    for (int c = 0; c < HD_MAXC; ++c) {
       if (c < C) {
-        const float lp = lg[j] - lse;
+        const float lp = lg[c] - lse;
         if (a.logp && live) a.logp[(size_t)(row0 + r) * C + c] = lp;
         dl[r * HD_MAXC + c] = live ? (expf(lp) - (c == lab ? 1.f : 0.f)) * a.inv_b : 0.f;
         if (c == lab) lt = -lp;
+      } else {
+        dl[r * HD_MAXC + c] = 0.f;                         // classes past C: read (and discarded) by the dW loop below
       }
     }
-    lt += __shfl_xor_sync(0xffffffffu, lt, 1); lt += __shfl_xor_sync(0xffffffffu, lt, 2);
-    if (q == 0) red[r] = live ? lt : 0.f;
+    red[r] = live ? lt : 0.f;
   }
   __syncthreads();
-  // dh = dlogits . W
+  // ---- dh = dlogits . W: thread = one 4-unit column group, eight rows at once
   if (a.dh) {
-    for (int i = tid; i < HD_ROWS * (H / 4); i += HD_THREADS) {
-      const int r = i / (H / 4), c4 = i - r * (H / 4);
-      if (row0 + r >= a.B) continue;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = 0; c < C; ++c) {
-        const float d = dl[r * HD_MAXC + c];
-        const float4 wv = *reinterpret_cast<const float4*>(Ws + c * H + c4 * 4);
-        acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y); acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
+    for (int k4 = tid % 32; k4 < H4; k4 += 32) {
+      for (int r0 = tid / 32; r0 < HD_ROWS; r0 += HD_THREADS / 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < C; ++c) {
+          const float dv = dl[r0 * HD_MAXC + c];
+          const float4 wv = *reinterpret_cast<const float4*>(Ws + c * Hp + k4 * 4);
+          acc.x = fmaf(dv, wv.x, acc.x); acc.y = fmaf(dv, wv.y, acc.y); acc.z = fmaf(dv, wv.z, acc.z); acc.w = fmaf(dv, wv.w, acc.w);
+        }
+        if (row0 + r0 < a.B) *(reinterpret_cast<float4*>(a.dh + (int64_t)(row0 + r0) * a.dh_stride) + k4) = acc;
       }
-      *(reinterpret_cast<float4*>(a.dh + (int64_t)(row0 + r) * a.dh_stride) + c4) = acc;
     }
   }
-  // per-CTA partials: dW[c][k] = sum_r dl[r][c] * h[r][k], db[c], loss
+  // ---- per-CTA partials: dW[c][k] = sum_r dl[r][c] * h[r][k] (thread = unit k x a class parity, all its classes at once), db[c], loss
   float* part = a.partial + (size_t)blockIdx.x * (C * H + C + 1);
-  for (int i = tid; i < C * H; i += HD_THREADS) {
-    const int c = i / H, k = i - c * H;
-    float s = 0.f;
-    for (int r = 0; r < HD_ROWS; ++r) s = fmaf(dl[r * HD_MAXC + c], hs[r * Hp + k], s);
-    part[i] = s;
+  for (int k = tid % 128; k < H; k += 128) {
+    const int c0 = tid / 128;                          // 0 or 1: this thread takes classes c0, c0 + 2, ...
+    float acc[HD_MAXC / 2];
+#pragma unroll
+    for (int j = 0; j < HD_MAXC / 2; ++j) acc[j] = 0.f;
+    for (int r = 0; r < HD_ROWS; ++r) {
+      const float hv = hs[r * Hp + k];
+#pragma unroll
+      for (int j = 0; j < HD_MAXC / 2; ++j) acc[j] = fmaf(dl[r * HD_MAXC + c0 + 2 * j], hv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < HD_MAXC / 2; ++j)
+      if (c0 + 2 * j < C) part[(c0 + 2 * j) * H + k] = acc[j];
   }
   if (tid < C) {
     float s = 0.f;
@@ -121,8 +144,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_nll_kernel(const HeadArgs a) 
   __threadfence();
   const int n = C * H + C + 1;
   for (int i = tid; i < n; i += HD_THREADS) {
-    // fixed order (run-to-run identical), sixteen independent loads in flight per thread: a plain `s += partial[g]` loop
-    // serialises the L2 round trips (measured 43 us for the whole kernel at 32 CTAs)
+    // fixed order (run-to-run identical), sixteen independent loads in flight per thread
     float s = 0.f;
     for (unsigned g0 = 0; g0 < gridDim.x; g0 += 16) {
       float v[16];
@@ -184,7 +206,7 @@ extern "C" int fgrnn_head_nll(const float* h, int64_t h_stride, const float* W, 
   a.counter = static_cast<unsigned*>(workspace);                      // first 256 bytes: the CTA counter (zero between launches)
   a.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   a.B = B; a.H = H; a.C = C; a.inv_b = 1.0f / (float)B;
-  const size_t smem = ((size_t)C * H + (size_t)HD_ROWS * (H + 4) + HD_ROWS * HD_MAXC + HD_ROWS) * sizeof(float);
+  const size_t smem = ((size_t)C * (H + 4) + (size_t)HD_ROWS * (H + 4) + HD_ROWS * HD_MAXC + HD_ROWS) * sizeof(float);
   FGRNN_CUDA_TRY(cudaFuncSetAttribute(head_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   head_nll_kernel<<<(unsigned)((B + HD_ROWS - 1) / HD_ROWS), HD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
   FGRNN_LAUNCH_CHECK("head_nll_kernel");

@@ -6,7 +6,10 @@
 2. data-parallel training: FastGRNN gradients in one flat bucket, summed with ONE NCCL all-reduce and divided by the
    world size == the gradients of a single-GPU run over the concatenated batch (rtol 1e-4 with the per-tensor atol floor
    of the north star), for every parameter;
-3. the same step replayed as one CUDA graph with the all-reduce captured on its own communicator == the eager step.
+3. the same step replayed as one CUDA graph with the all-reduce captured on its own communicator == the eager step;
+4. the keyword spotter's step on the last state (kws_b200.train_step.LastStateTrainStep: fused head + loss kernel, BPTT from
+   the last state's gradient, ONE all-reduce of the flat bucket, flat SGD with the 1 / world folded in): two data-parallel
+   steps leave every rank with the parameters of two single-GPU steps over the concatenated batch.
 Prints "DIST_CHECK ok" on rank 0; any mismatch raises."""
 import os
 import sys
@@ -16,7 +19,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from kws_b200 import graphs, rnn, sharding  # noqa: E402
+from kws_b200 import graphs, rnn, sharding, train_step  # noqa: E402
 
 
 def grad_ratio(got, ref, rtol=1e-4):
@@ -89,9 +92,32 @@ def main():
     assert torch.equal(bucket.flat, eager), "rank %d: captured data-parallel step differs from the eager one" % rank
     del cap                                   # a live graph that holds a captured collective blocks the communicator teardown
     torch.cuda.synchronize()
+
+    # ---- 4. the fused last-state training step, data parallel vs one GPU on the concatenated batch
+    def make_model():
+        torch.manual_seed(5)
+        return rnn.FastGRNN(I, H).to(dev), torch.nn.Linear(H, 13).to(dev)
+    labels_all = torch.randint(0, 13, (Bg,), generator=g).to(dev)
+    x2_all = torch.randn(T, Bg, I, generator=g).to(dev)
+    l_ref, h_ref = make_model()
+    ref_step = train_step.LastStateTrainStep(l_ref, h_ref, 0.05, data_parallel=False)
+    l_dp, h_dp = make_model()
+    sharding.broadcast_parameters(list(l_dp.cell.parameters()) + list(h_dp.parameters()))
+    dp_step = train_step.LastStateTrainStep(l_dp, h_dp, 0.05, data_parallel=True)
+    assert dp_step.world == world
+    for xa in (x_all, x2_all):
+        loss_ref = ref_step(xa, labels_all)
+        loss_dp = dp_step(xa[:, b:e].contiguous(), labels_all[b:e].contiguous())
+        lsum = loss_dp.clone()
+        dist.all_reduce(lsum)
+        assert abs(float(lsum) / world - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)) + 1e-6, "rank %d: mean of the rank losses differs" % rank
+    torch.cuda.synchronize()
+    worst_p = float(((dp_step.flat_params - ref_step.flat_params).abs() / (1e-6 + 1e-5 * ref_step.flat_params.abs())).max())
+    assert worst_p <= 1.0, "rank %d: parameters after two data-parallel fused steps off by %.3f x (rtol 1e-5, atol 1e-6)" % (rank, worst_p)
     dist.barrier(device_ids=[local])
     if rank == 0:
-        print("DIST_CHECK ok: world %d, sharded inference bitwise, all-reduced gradients at %.3f of tolerance, captured step bitwise" % (world, worst), flush=True)
+        print("DIST_CHECK ok: world %d, sharded inference bitwise, all-reduced gradients at %.3f of tolerance, captured step bitwise, "
+              "fused last-state step parameters at %.3f of (1e-5, 1e-6)" % (world, worst, worst_p), flush=True)
     sys.stdout.flush()
     os._exit(0)                               # skip the process-group teardown: nothing left to do, and it must never hang a test
 
