@@ -22,7 +22,7 @@ void set_error_detail(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR", "FGRNN_TC_ALT", "FGRNN_TC_ACC2", "FGRNN_TC_BWD_FUSED"};
+static const char* const kTuneNames[TUNE_COUNT] = {"FGRNN_TC_NS", "FGRNN_TC_NT", "FGRNN_TC_BR_NS", "FGRNN_TC_WIDE", "FGRNN_FAST_NL", "FGRNN_SMEM_CFG", "FGRNN_TC_LR", "FGRNN_TC_ALT", "FGRNN_TC_ACC2", "FGRNN_TC_BWD_FUSED", "FGRNN_TC_VR"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::once_flag g_tune_once;
 static int tune_parse(int key, const char* e) {
@@ -134,6 +134,10 @@ bool fits_u32_bytes(int64_t elems) { return elems >= 0 && elems < ((int64_t)1 <<
 // tcgen05 family: same streaming requirements; x is fetched by TMA (16-byte aligned base and strides)
 bool tc_fwd_ok(const FgrnnForward& f) {
   const FgrnnProblem& p = f.p;
+  // h_t, z_t, c_t leave through TMA tile stores: positive output strides (alignment: smem_fwd_ok); the three staging tiles of a
+  // training forward do not fit beside the operand rings of I > 32
+  if (f.out && (f.out_stride_b <= 0 || f.out_stride_t <= 0)) return false;
+  if (f.save_z && p.I > 32) return false;
   return smem_fwd_ok(f) && tc_path_supports(dims_of(p)) &&
          tc_x_tma_ok(p.x, p.x_stride_b, p.x_stride_t, p.x_dtype, p.B, p.T) &&
          fits_u32_bytes(f.out_stride_b) && fits_u32_bytes(f.out_stride_t) && fits_u32_bytes((int64_t)p.B * p.H);

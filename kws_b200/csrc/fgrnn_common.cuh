@@ -22,7 +22,7 @@ void count_launch(int n = 1);
 
 // Tuning / test overrides of the launchers.  Each key takes its default from the environment variable of the same name,
 // read ONCE per process (no getenv on the launch path); fgrnn_debug_set_tuning changes it afterwards (tests).
-enum TuneKey { TUNE_TC_NS = 0, TUNE_TC_NT, TUNE_TC_BR_NS, TUNE_TC_WIDE, TUNE_FAST_NL, TUNE_SMEM_CFG, TUNE_TC_LR, TUNE_TC_ALT, TUNE_TC_ACC2, TUNE_TC_BWD_FUSED, TUNE_COUNT };
+enum TuneKey { TUNE_TC_NS = 0, TUNE_TC_NT, TUNE_TC_BR_NS, TUNE_TC_WIDE, TUNE_FAST_NL, TUNE_SMEM_CFG, TUNE_TC_LR, TUNE_TC_ALT, TUNE_TC_ACC2, TUNE_TC_BWD_FUSED, TUNE_TC_VR, TUNE_COUNT };
 constexpr int TUNE_UNSET = -2147483647 - 1;
 int tuning(TuneKey key);          // TUNE_UNSET when neither the environment nor a test set it
 

@@ -70,6 +70,10 @@ constexpr int TC_TMEM_COLS = 512;
 #ifndef TC_STAGGER_NS
 #define TC_STAGGER_NS 500
 #endif
+#ifndef TC_TMA_STORE
+#define TC_TMA_STORE 2          // 1 / 2: h_t (and z_t, c_t) leave through per-warp staging tiles and TMA tile stores (2: h_t is staged
+                                // after the hand-off to the tensor core); 0: scalar st.global
+#endif
 
 // Developer trace (tools/tc_trace.cu defines FGRNN_TC_TRACE): clock64 stamps of CTA 0 for steps [16, 20)
 #ifdef FGRNN_TC_TRACE
@@ -91,10 +95,11 @@ struct TcArgs {
   SmemFwdArgs f;
   int KI;               // I rounded up to a multiple of 16
   int x_time_outer;     // tensor-map dimension order: 0 = {I, T, B}, 1 = {I, B, T}
+  int o_time_outer;     // the same for the output map (TMA stores)
 };
 
 struct TcSmemLayout {
-  int h_op, x_op, raw, bars, misc, total;
+  int h_op, x_op, raw, stage, bars, misc, total;
   int x_tile_bytes, raw_stage_bytes;
 };
 // Everything below depends on the sub-tile width NS = UMMA N (32 rows for large batches; 16 rows when the batch
@@ -112,7 +117,12 @@ struct TcSmemLayout {
 // small lose nothing: the emulator (tools/emulate_tc_schemes.py lofirst2) puts this order at 0.55-0.63 of the tolerance, the
 // same as the four-accumulator scheme (0.54-0.62) -- and the epilogue reads half as much tensor memory per element
 // (tcgen05.ld of four accumulators was the largest single cost of the epilogue).
-template <int TC_NS, int TC_NT, bool ALT = false, bool ACC2 = false>
+// VR_ (0 = all): VALID rows per epilogue thread.  The CTA's row groups (one per converter warp = one per (sub-tile, row part)
+// of the epilogue) each hold VR rows in the first VR of their RPT accumulator columns; the other columns are padding (zero x,
+// zero h: batch rows are independent columns of the MMA, so the padding touches nothing).  An MMA costs the same for any
+// N <= 32, so 8192 rows can run as 147 CTAs of 4 x 14 rows (all SMs busy) instead of 128 CTAs of 4 x 16 -- with the very same
+// arithmetic per row.  Measured: no faster (launch_tc_fwd), opt-in.
+template <int TC_NS, int TC_NT, bool ALT = false, bool ACC2 = false, int VR_ = 0>
 struct TcFwd {
 static_assert(!ACC2 || TC_NT == 2, "ACC2: two sub-tiles");
 static_assert(TC_NT == 2 || (TC_NT == 4 && TC_NS == 16), "sub-tile configuration");
@@ -129,6 +139,16 @@ static constexpr int TM_ACC_PER_TILE = 4 * TC_NS;      // CA | CB | M1 | M2
 static constexpr int RPT = TC_NS / TC_RH;              // rows per epilogue thread
 static constexpr int PAIRS = RPT / 2;                  // row pairs on the packed fp32x2 pipe
 static constexpr int NG = RPT / 8;                     // 8-row groups = 16-byte operand chunks per thread
+static constexpr int VR = VR_ ? VR_ : RPT;             // valid rows per epilogue thread
+static constexpr int VPAIRS = VR / 2;
+static constexpr int CONV_VROWS = TC_CONV_ROWS / RPT * VR;     // valid rows per converter warp / TMA box
+static constexpr int TC_VROWS = TC_ROWS / RPT * VR;            // batch rows per CTA
+static_assert(VR % 2 == 0 && VR <= RPT && (VR == RPT || (!ALT && TC_CONV_ROWS == RPT)), "valid rows per thread");
+// TMA stores: every epilogue warp owns staging tiles [h | z | c][RPT rows][32 units] fp32 (lane = unit: 128 contiguous bytes per
+// row, conflict-free, immediate offsets) and one lane ships each as a {32, RPT} box; rows past the batch end are clipped by the
+// TMA unit.  A scalar store costs four issue slots (IMAD.WIDE + 2 MOV + STG) in a kernel that is bound by them.
+static constexpr bool TMA_ST = TC_TMA_STORE != 0 && !ALT;
+static constexpr int STAGE_TILE = RPT * 32 * 4;
 
 // ---- operand layouts (SWIZZLE_NONE canonical layouts, 128-byte core matrices) -------------------
 // x tile, K-major [rows][KI]: core matrix = 8 rows x 16 B (8 k);  next 8 k: +128 B (LBO);  next 8 rows: +(KI/8)*128 B (SBO)
@@ -148,16 +168,16 @@ static constexpr uint32_t TC_IDESC_X = (1u << 4) | ((uint32_t)(TC_NS >> 3) << 17
 static constexpr uint32_t TC_IDESC_H = TC_IDESC_X | (1u << 16);
 
 
-static __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz) {
+static __host__ __device__ inline TcSmemLayout tc_smem_layout(int I, int KI, int esz, bool save) {
   TcSmemLayout L;
   L.x_tile_bytes = TC_NS * KI * 2;
-  L.raw_stage_bytes = TC_CONV_ROWS * I * esz;                   // per converter warp
+  L.raw_stage_bytes = (CONV_VROWS * I * esz + 127) & ~127;      // per converter warp; a TMA destination is 128-byte aligned
   L.h_op = 0;                                                   // [NT][hi|lo][NS*128*2]
   L.x_op = L.h_op + TC_NT * 2 * TC_NS * TC_H * 2;               // [XBUF][NT][hi|lo][x_tile_bytes]
   L.raw = L.x_op + TC_XBUF * TC_NT * 2 * L.x_tile_bytes;        // [CONV_WARPS][RAW_STAGES][raw_stage_bytes], 128-byte aligned
   L.raw = (L.raw + 127) & ~127;
-  L.bars = L.raw + TC_CONV_WARPS * TC_RAW_STAGES * L.raw_stage_bytes;
-  L.bars = (L.bars + 15) & ~15;
+  L.stage = (L.raw + TC_CONV_WARPS * TC_RAW_STAGES * L.raw_stage_bytes + 127) & ~127;      // [epilogue warp][h | z | c][STAGE_TILE]
+  L.bars = L.stage + (TMA_ST ? TC_EPI_WARPS * (save ? 3 : 1) * STAGE_TILE : 0);
   L.misc = L.bars + 32 * 8;
   L.total = L.misc + 256;
   return L;
@@ -241,6 +261,10 @@ struct EpiCtx {
   int rows_left;                      // B - first row of this thread: rows >= rows_left are padding
   int T, s;
   bool trace;
+  // TMA stores
+  const CUtensorMap *omap, *zmap, *cmap;
+  float* stage;                       // this warp's staging tiles, this lane's column
+  int o_unit0, o_row0, o_time_outer;  // box origin: first unit of the warp, first row
 };
 
 template <bool HAS_OUT, bool SAVE, bool MASKED, bool ONE_EX2>
@@ -255,7 +279,13 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
 #endif
     tc_fence_after();
     if (cx.trace) TC_TRACE(t, cx.s, 1);
+    if (TMA_ST && (HAS_OUT || SAVE)) {                 // the stores of step t-1 have read the staging tiles (issued a whole MMA burst ago)
+      if ((threadIdx.x & 31) == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
     uint32_t hi[PAIRS], lo[PAIRS];
+#pragma unroll
+    for (int q = VPAIRS; q < PAIRS; ++q) { hi[q] = 0u; lo[q] = 0u; }      // padding columns
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       float va[8], vb[8], v1[8], v2[8];
@@ -269,6 +299,7 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
       if (cx.trace && g == 0) TC_TRACE(t, cx.s, 2);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        if (g * 4 + q >= VPAIRS) continue;
         const float2 corr = __fadd2_rn(make_float2(va[2 * q], va[2 * q + 1]), make_float2(vb[2 * q], vb[2 * q + 1]));     // ACC2: X + Y
         const float2 tot = ACC2 ? corr : __fadd2_rn(__fadd2_rn(corr, make_float2(v2[2 * q], v2[2 * q + 1])), make_float2(v1[2 * q], v1[2 * q + 1]));
         float2 z, c;
@@ -278,7 +309,11 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
         hst[g * 4 + q] = gate_update2<ONE_EX2>(tot, hst[g * 4 + q], kc, z, c);
 #endif
         split_pair(hst[g * 4 + q], hi[g * 4 + q], lo[g * 4 + q]);
-        if (SAVE) {                                      // training forward: z_s, c_s (cu:340-341)
+        if (SAVE && TMA_ST) {                            // training forward: z_s, c_s (cu:340-341) through the staging tiles
+          const int rj = g * 8 + 2 * q;
+          cx.stage[STAGE_TILE / 4 + rj * 32] = z.x; cx.stage[STAGE_TILE / 4 + (rj + 1) * 32] = z.y;
+          cx.stage[2 * (STAGE_TILE / 4) + rj * 32] = c.x; cx.stage[2 * (STAGE_TILE / 4) + (rj + 1) * 32] = c.y;
+        } else if (SAVE) {
           const int rj = g * 8 + 2 * q;
           if (!MASKED || rj < cx.rows_left) { zp[rj * TC_H] = z.x; cp[rj * TC_H] = c.x; }
           if (!MASKED || rj + 1 < cx.rows_left) { zp[(rj + 1) * TC_H] = z.y; cp[(rj + 1) * TC_H] = c.y; }
@@ -290,24 +325,51 @@ static __device__ __forceinline__ void epilogue_loop(const EpiCtx& cx, const Epi
       *reinterpret_cast<uint4*>(cx.hop + g * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
       *reinterpret_cast<uint4*>(cx.hop + TC_NS * TC_H * 2 + g * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
     }
+    if (HAS_OUT && TMA_ST && TC_TMA_STORE == 1) {      // staging before the hand-off: one fence serves both
+#pragma unroll
+      for (int q = 0; q < VPAIRS; ++q) { cx.stage[(2 * q) * 32] = hst[q].x; cx.stage[(2 * q + 1) * 32] = hst[q].y; }
+    }
     if (cx.trace) TC_TRACE(t, cx.s, 3);
     // hand h_t to the tensor core first: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would
     // wait for the global stores too, so those are issued after the arrive and drain behind the next wait
-    fence_proxy_async_smem();                          // st.shared of the h tile -> visible to tcgen05.mma
+    fence_proxy_async_smem();                          // st.shared of the h tile (and the staging tiles) -> visible to the async proxy
     tc_fence_before();                                 // tcgen05.ld of D done before the next MMAs overwrite it
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready);
     if (cx.trace) TC_TRACE(t, cx.s, 4);
-    if (HAS_OUT) {
+    if (TMA_ST && (HAS_OUT || SAVE)) {
+      if (HAS_OUT && TC_TMA_STORE == 2) {              // staging after the hand-off: off the step-critical chain, a fence of its own
 #pragma unroll
-      for (int q = 0; q < PAIRS; ++q) {
+        for (int q = 0; q < VPAIRS; ++q) { cx.stage[(2 * q) * 32] = hst[q].x; cx.stage[(2 * q + 1) * 32] = hst[q].y; }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t src = smem_u32(cx.stage);       // lane 0: the tile base
+        if (HAS_OUT) {
+          if (cx.o_time_outer) tma_store_3d(cx.omap, cx.o_unit0, cx.o_row0, t, src);
+          else tma_store_3d(cx.omap, cx.o_unit0, t, cx.o_row0, src);
+        }
+        if (SAVE) {
+          tma_store_3d(cx.zmap, cx.o_unit0, cx.o_row0, t, src + STAGE_TILE);
+          tma_store_3d(cx.cmap, cx.o_unit0, cx.o_row0, t, src + 2 * STAGE_TILE);
+        }
+        tma_store_commit();
+      }
+    } else if (HAS_OUT) {
+#pragma unroll
+      for (int q = 0; q < VPAIRS; ++q) {
         if (!MASKED || 2 * q < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q) * row_bytes) = hst[q].x;
         if (!MASKED || 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(outp + (size_t)(2 * q + 1) * row_bytes) = hst[q].y;
       }
       outp += (size_t)cx.out_step * 4u;
     }
     if (cx.trace) TC_TRACE(t, cx.s, 5);
-    if (SAVE) { zp += cx.zc_step; cp += cx.zc_step; }
+    if (SAVE && !TMA_ST) { zp += cx.zc_step; cp += cx.zc_step; }
+  }
+  if (TMA_ST && (HAS_OUT || SAVE)) {
+    if ((threadIdx.x & 31) == 0) tma_store_wait_all();
+    __syncwarp();
   }
 }
 
@@ -444,13 +506,14 @@ static __device__ __forceinline__ void issue_subtile_dispatch(int variant, uint3
   }
 }
 
-static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& xmap) {
+static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& xmap, const CUtensorMap& omap, const CUtensorMap& zmap,
+                                           const CUtensorMap& cmap) {
   extern __shared__ __align__(128) unsigned char sm[];
   const SmemFwdArgs& a = ta.f;
   const Dims d = a.d;
   const int I = d.I, KI = ta.KI;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
-  const TcSmemLayout L = tc_smem_layout(I, KI, esz);
+  const TcSmemLayout L = tc_smem_layout(I, KI, esz, a.save_z != nullptr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
   float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16] max|U|, max|W|, max|b_g - b_u| per epilogue warp
@@ -458,7 +521,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
   // warp index through a shuffle: the compiler then knows it is warp uniform and keeps everything derived from it
   // (MMA set / role, descriptors, barrier addresses) in uniform registers instead of R2UR-ing it per instruction
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int row0 = blockIdx.x * TC_ROWS;
+  const int row0 = blockIdx.x * TC_VROWS;
   const bool hi_layout = a.layout == FGRNN_LAYOUT_HI;
   // barrier map
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
@@ -563,9 +626,9 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     // Each converter warp owns 16 rows of the CTA's 64: its own TMA box, raw ring and barriers, so the four
     // never wait for one another.  The (row, 8-feature chunk) -> address mapping is step-invariant.
     const int cw = warp - W_CONV0;
-    const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
+    const uint32_t raw_bytes = (uint32_t)(CONV_VROWS * I * esz);           // bytes of one TMA box
     unsigned char* raw_base = sm + L.raw + cw * TC_RAW_STAGES * L.raw_stage_bytes;
-    const int my_row0 = row0 + cw * TC_CONV_ROWS;
+    const int my_row0 = row0 + cw * CONV_VROWS;
     auto issue_tma = [&](int t) {
       const int st = t % TC_RAW_STAGES;
       const uint32_t fb = bar(B_RAWFULL + cw * TC_RAW_STAGES + st);
@@ -586,7 +649,7 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
       const int e = it * 32 + lane;
       const int row = e / nch, ch = e - row * nch;
       live[it] = e < ntask;
-      pad[it] = ch * 8 >= I;                                     // K padding chunk: zeros
+      pad[it] = ch * 8 >= I || row >= CONV_VROWS;                // K padding chunk, padding row: zeros
       src_off[it] = (uint32_t)(row * I * esz + ch * 8 * esz);
       const int R = cw * TC_CONV_ROWS + row, sidx = R / TC_NS, r = R - sidx * TC_NS;
       dst_off[it] = (uint32_t)((sidx * 2) * L.x_tile_bytes + (r >> 3) * (nch * 128) + ch * 128 + (r & 7) * 16);
@@ -800,14 +863,14 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     // state: this thread owns h[row][n] for 16 rows of its sub-tile, kept as row pairs for the fp32x2 pipe
     float2 hst[PAIRS];
     unsigned char* hop = sm + L.h_op + es * (2 * TC_NS * TC_H * 2) + (n >> 3) * ((TC_NS >> 3) * 128) + (rh * NG) * 128 + (n & 7) * 16;
-    const int first_row = row0 + es * TC_NS + rh * RPT;
+    const int first_row = row0 + (es * TC_RH + rh) * VR;
     {
       uint32_t hi[PAIRS], lo[PAIRS];
 #pragma unroll
       for (int q = 0; q < PAIRS; ++q) {
         const int row = first_row + 2 * q;
-        const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
-        const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
+        const float v0 = (a.h0 && q < VPAIRS && row < d.B) ? __ldg(a.h0 + (size_t)row * TC_H + n) : 0.f;
+        const float v1 = (a.h0 && q < VPAIRS && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TC_H + n) : 0.f;
         hst[q] = make_float2(v0, v1);
         split2(v0, v1, 1.0f, hi[q], lo[q]);
       }
@@ -833,30 +896,33 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
     cx.cs = a.save_c ? a.save_c + (size_t)first_row * TC_H + n : nullptr;
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost; cx.zc_step = (uint32_t)d.B * TC_H;
     cx.rows_left = d.B - first_row; cx.T = d.T; cx.trace = (ew & 11) == 0; cx.s = es;
-    const bool masked = row0 + TC_ROWS > d.B;
+    cx.omap = &omap; cx.zmap = &zmap; cx.cmap = &cmap;
+    cx.stage = reinterpret_cast<float*>(sm + L.stage) + ew * (a.save_z ? 3 : 1) * (STAGE_TILE / 4) + lane;
+    cx.o_unit0 = quad * 32; cx.o_row0 = first_row; cx.o_time_outer = ta.o_time_outer;
+    const bool masked = !TMA_ST && row0 + TC_VROWS > d.B;       // the TMA unit clips the boxes at the batch end
     const int variant = (one_ex2 ? 8 : 0) | (a.out ? 4 : 0) | (a.save_z ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
       case 0: epilogue_loop<false, false, false, false>(cx, kc, hst); break;
-      case 1: epilogue_loop<false, false, true, false>(cx, kc, hst); break;
+      case 1: if constexpr (!TMA_ST) epilogue_loop<false, false, true, false>(cx, kc, hst); break;
       case 2: epilogue_loop<false, true, false, false>(cx, kc, hst); break;
-      case 3: epilogue_loop<false, true, true, false>(cx, kc, hst); break;
+      case 3: if constexpr (!TMA_ST) epilogue_loop<false, true, true, false>(cx, kc, hst); break;
       case 4: epilogue_loop<true, false, false, false>(cx, kc, hst); break;
-      case 5: epilogue_loop<true, false, true, false>(cx, kc, hst); break;
+      case 5: if constexpr (!TMA_ST) epilogue_loop<true, false, true, false>(cx, kc, hst); break;
       case 6: epilogue_loop<true, true, false, false>(cx, kc, hst); break;
-      case 7: epilogue_loop<true, true, true, false>(cx, kc, hst); break;
+      case 7: if constexpr (!TMA_ST) epilogue_loop<true, true, true, false>(cx, kc, hst); break;
       case 8: epilogue_loop<false, false, false, true>(cx, kc, hst); break;
-      case 9: epilogue_loop<false, false, true, true>(cx, kc, hst); break;
+      case 9: if constexpr (!TMA_ST) epilogue_loop<false, false, true, true>(cx, kc, hst); break;
       case 10: epilogue_loop<false, true, false, true>(cx, kc, hst); break;
-      case 11: epilogue_loop<false, true, true, true>(cx, kc, hst); break;
+      case 11: if constexpr (!TMA_ST) epilogue_loop<false, true, true, true>(cx, kc, hst); break;
       case 12: epilogue_loop<true, false, false, true>(cx, kc, hst); break;
-      case 13: epilogue_loop<true, false, true, true>(cx, kc, hst); break;
+      case 13: if constexpr (!TMA_ST) epilogue_loop<true, false, true, true>(cx, kc, hst); break;
       case 14: epilogue_loop<true, true, false, true>(cx, kc, hst); break;
-      default: epilogue_loop<true, true, true, true>(cx, kc, hst); break;
+      default: if constexpr (!TMA_ST) epilogue_loop<true, true, true, true>(cx, kc, hst); break;
     }
     TC_CTA_TIME(2);
     if (a.h_last) {
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) {
+      for (int j = 0; j < VR; ++j) {
         const int row = first_row + j;
         if (row < d.B) a.h_last[(size_t)row * TC_H + n] = (j & 1) ? hst[j >> 1].y : hst[j >> 1].x;
       }
@@ -870,9 +936,11 @@ static __device__ __forceinline__ void run(const TcArgs& ta, const CUtensorMap& 
 
 };   // struct TcFwd
 
-template <int NS, int NT, bool ALT = false, bool ACC2 = false>
-__global__ void __launch_bounds__((TcFwd<NS, NT, ALT, ACC2>::TC_THREADS), 1) tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap) {
-  TcFwd<NS, NT, ALT, ACC2>::run(ta, xmap);
+template <int NS, int NT, bool ALT = false, bool ACC2 = false, int VR = 0>
+__global__ void __launch_bounds__((TcFwd<NS, NT, ALT, ACC2, VR>::TC_THREADS), 1)
+tc_fwd_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap omap,
+              const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap cmap) {
+  TcFwd<NS, NT, ALT, ACC2, VR>::run(ta, xmap, omap, zmap, cmap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -897,21 +965,31 @@ bool tc_x_tma_ok(const void* x, int64_t xsb, int64_t xst, int x_dtype, int B, in
   return xsb > 0 && xst > 0;
 }
 
-template <int NS, int NT, bool ALT = false, bool ACC2 = false>
+template <int NS, int NT, bool ALT = false, bool ACC2 = false, int VR = 0>
 static int launch_tc_fwd_ns(const SmemFwdArgs& a, cudaStream_t stream) {
-  using K = TcFwd<NS, NT, ALT, ACC2>;
+  using K = TcFwd<NS, NT, ALT, ACC2, VR>;
   const Dims& d = a.d;
   TcArgs ta{};
   ta.f = a;
   ta.KI = (d.I + 15) & ~15;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
   CUtensorMap map;
-  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, K::TC_CONV_ROWS, &ta.x_time_outer);
+  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, K::CONV_VROWS, &ta.x_time_outer);
   if (rc) return rc;
-  const TcSmemLayout L = K::tc_smem_layout(d.I, ta.KI, esz);
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS, NT, ALT, ACC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  const unsigned grid = (unsigned)((d.B + K::TC_ROWS - 1) / K::TC_ROWS);
-  tc_fwd_kernel<NS, NT, ALT, ACC2><<<grid, K::TC_THREADS, L.total, stream>>>(ta, map);
+  CUtensorMap omap = map, zmap = map, cmap = map;      // valid descriptors even where a tensor is absent
+  if (K::TMA_ST) {
+    int to = 1;
+    if (a.out) { const int r2 = make_row_tile_map(&omap, a.out, false, TC_H, d.B, d.T, a.osb, a.ost, K::VR, &ta.o_time_outer, 32); if (r2) return r2; }
+    if (a.save_z) {                                    // [T][B][H] contiguous
+      int r2 = make_row_tile_map(&zmap, a.save_z, false, TC_H, d.B, d.T, TC_H, (int64_t)d.B * TC_H, K::VR, &to, 32);
+      if (!r2) r2 = make_row_tile_map(&cmap, a.save_c, false, TC_H, d.B, d.T, TC_H, (int64_t)d.B * TC_H, K::VR, &to, 32);
+      if (r2) return r2;
+    }
+  }
+  const TcSmemLayout L = K::tc_smem_layout(d.I, ta.KI, esz, a.save_z != nullptr);
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_fwd_kernel<NS, NT, ALT, ACC2, VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const unsigned grid = (unsigned)((d.B + K::TC_VROWS - 1) / K::TC_VROWS);
+  tc_fwd_kernel<NS, NT, ALT, ACC2, VR><<<grid, K::TC_THREADS, L.total, stream>>>(ta, map, omap, zmap, cmap);
   FGRNN_LAUNCH_CHECK("tc_fwd_kernel");
   return FGRNN_OK;
 }
@@ -936,6 +1014,10 @@ int launch_tc_fwd(const SmemFwdArgs& a, cudaStream_t stream) {
   // shard runs 16-row sub-tiles, the 8192-row batch 32-row ones; tests/test_gpu_fullsize.py compares them bit for bit).
   // Sixteen epilogue warps alternating between the sub-tiles (FGRNN_TC_ALT=1) is bit-identical but 3-5 % slower: opt-in too.
   const bool acc2 = tuning(TUNE_TC_ACC2) == 1, alt = tuning(TUNE_TC_ALT) == 1;
+  // FGRNN_TC_VR=14: 56-row CTAs (TcFwd: VR_; 8192 rows then fill 147 SMs instead of 128).  Bit-identical, and measured on C2 / C5
+  // (same box, A/B): 0.1504 -> 0.1496 ms / 1.332 -> 1.353 ms -- the per-step chain of a CTA does not get shorter with fewer rows
+  // per epilogue thread, so more CTAs of fewer rows buy nothing here (they do in the low-rank kernel, fgrnn_tc_lr.cu).  Opt-in.
+  if (ns == 32 && !acc2 && !alt && tuning(TUNE_TC_VR) == 14) return launch_tc_fwd_ns<32, 2, false, false, 14>(a, stream);
   if (ns == 16) return acc2 ? launch_tc_fwd_ns<16, 2, false, true>(a, stream) : launch_tc_fwd_ns<16, 2>(a, stream);
   if (acc2) return alt ? launch_tc_fwd_ns<32, 2, true, true>(a, stream) : launch_tc_fwd_ns<32, 2, false, true>(a, stream);
   return alt ? launch_tc_fwd_ns<32, 2, true>(a, stream) : launch_tc_fwd_ns<32, 2>(a, stream);

@@ -203,6 +203,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
                ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
+// TMA tile store shared -> global (bulk async-group completion).  The source tile must have been made visible to the async
+// proxy (fence.proxy.async after the st.shared) by every writing thread before the issuing thread gets here.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(src_smem) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // v*scale = hi + lo with hi, lo fp16 (round to nearest); two values at once.  No clamp: NaN stays NaN and a value
 // beyond the fp16 range (|v*scale| > 65504; weights are pre-scaled below 30000, so this means an input or state of
 // that size) becomes Inf - Inf = NaN in the lo part -- the result is NaN, as loud as the reference's own NaN/Inf

@@ -14,8 +14,11 @@
 // Warp roles (24 warps): 0..15 epilogue -- ALL of them serve both sub-tiles in turn (thread = hidden unit x 16 rows of
 // each sub-tile), so that a sub-tile's epilogue has four warps per scheduler behind it: the per-step chain of a sub-tile
 // (stage 1 -> hop -> stage 2 -> epilogue) is what bounds the kernel, and with eight warps per sub-tile the epilogue alone
-// was half of it (tools/trace_lowrank.py); 16..18 hop (lane quadrants 0..2, no global stores in flight when they
-// fence); 19..20 x path (TMA -> fp16 split, one sub-tile each); 21..24 MMA issue ([sub-tile][role]).
+// was half of it (tools/trace_lowrank.py); 16..18 hop (lane quadrants 0..2, no global stores in flight when they fence; six hop
+// warps -- one 16-row half of a sub-tile each, TL_HOP_HALVES=2 -- measured the same); 19..20 x path (TMA -> fp16 split, one
+// sub-tile each); 21..24 MMA issue ([sub-tile][role]).  h_t leaves through per-warp staging tiles and TMA tile stores
+// (TL_TMA_STORE, 1.146 -> 1.114 ms at C4: a scalar store costs four issue slots); the gate's reciprocal on the FMA pipe
+// instead of MUFU.RCP (TL_RCP_NEWTON) was measured 6 % slower and is off.
 //
 // Both weight sets stay in TENSOR MEMORY for the whole kernel: stage 1 takes 144 columns (hi and lo share them, on different
 // lanes), stage 2 96 (fp16 hi | lo).  D1 and D2 of a sub-tile are never live at the same time (D1 dies when
@@ -35,7 +38,16 @@ namespace fgrnn {
 
 constexpr int TL_H = 256, TL_NS = 32, TL_NT = 2, TL_ROWS = TL_NS * TL_NT;
 constexpr int TL_RU = 32, TL_RW = 16, TL_K2 = TL_RU + TL_RW;            // padded ranks; K of stage 2
-constexpr int TL_EPI_WARPS = 16, TL_HOP_WARPS = 3, TL_CONV_WARPS = 2, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
+#ifndef TL_HOP_HALVES
+#define TL_HOP_HALVES 1           // 1: three hop warps (one per lane quadrant) convert both 16-row halves of a sub-tile; 2: six, one half each
+#endif
+#ifndef TL_RCP_NEWTON
+#define TL_RCP_NEWTON 0           // 1: the reciprocal of the gate update on the FMA pipe (Newton) instead of MUFU.RCP
+#endif
+constexpr int TL_EPI_WARPS = 16, TL_HOP_WARPS = 3 * TL_HOP_HALVES, TL_CONV_WARPS = 2, TL_MMA_WARPS = 4;   // MMA warps: [sub-tile][role]
+#ifndef TL_TMA_STORE
+#define TL_TMA_STORE 1            // 1: h_t leaves through a per-warp staging tile and TMA tile stores; 0: scalar st.global per row
+#endif
 constexpr int TL_THREADS = 32 * (TL_EPI_WARPS + TL_HOP_WARPS + TL_CONV_WARPS + TL_MMA_WARPS);
 constexpr int TL_RPT = TL_NS / 2;                     // rows of each sub-tile per epilogue thread
 constexpr int TL_XBUF = 4, TL_RAW_STAGES = 4, TL_CONV_ROWS = TL_ROWS / TL_CONV_WARPS;
@@ -69,18 +81,21 @@ struct TlArgs {
   FwdArgs f;
   int KI;               // I rounded up to a multiple of 16 (16 or 32)
   int x_time_outer;
+  int o_time_outer;     // coordinate order of the output map (TL_TMA_STORE)
 };
-struct TlSmem { int h_op, s_op, x_op, raw, bars, misc, total; int x_tile_bytes, raw_stage_bytes; };
+struct TlSmem { int h_op, s_op, x_op, raw, stage, bars, misc, total; int x_tile_bytes, raw_stage_bytes; };
+constexpr int TL_STAGE_TILE = 16 * 32 * 4;            // one epilogue warp's h_t box: 16 rows x 32 units fp32
 
 __host__ __device__ inline TlSmem tl_smem_layout(int I, int KI, int esz) {
   TlSmem L;
   L.x_tile_bytes = TL_NS * KI * 2;
-  L.raw_stage_bytes = TL_CONV_ROWS * I * esz;
+  L.raw_stage_bytes = (TL_CONV_ROWS * I * esz + 127) & ~127;    // sized for whole sub-tiles; a TMA destination is 128-byte aligned
   L.h_op = 0;                                                   // [NT][hi|lo][TL_H_TILE]
   L.s_op = L.h_op + TL_NT * 2 * TL_H_TILE;                      // [NT][hi|lo][TL_S_TILE]
   L.x_op = L.s_op + TL_NT * 2 * TL_S_TILE;                      // [XBUF][NT][hi|lo][x_tile_bytes]
   L.raw = (L.x_op + TL_XBUF * TL_NT * 2 * L.x_tile_bytes + 127) & ~127;
-  L.bars = (L.raw + TL_CONV_WARPS * TL_RAW_STAGES * L.raw_stage_bytes + 15) & ~15;
+  L.stage = (L.raw + TL_CONV_WARPS * TL_RAW_STAGES * L.raw_stage_bytes + 127) & ~127;     // [epilogue warp][sub-tile][TL_STAGE_TILE]
+  L.bars = L.stage + (TL_TMA_STORE ? TL_EPI_WARPS * TL_NT * TL_STAGE_TILE : 0);
   L.misc = L.bars + 48 * 8;
   L.total = L.misc + 512;
   return L;
@@ -117,7 +132,16 @@ static __device__ __forceinline__ float2 tl_gate_update2(float2 tot, float2 h, c
   const float2 a = __fadd2_rn(eg, one), b = __fadd2_rn(eu, one);
   const float2 ab = __fmul2_rn(a, b);
   float2 r;
+#if TL_RCP_NEWTON
+  // 1 / ab on the FMA pipe (ab >= 1, finite): magic-constant estimate (<= 12 % off) + three Newton steps on the packed
+  // fp32x2 pipe, <= 1 ulp -- the MUFU unit (16 lanes per SM and clock) then only serves the one EX2 per element
+  r.x = __int_as_float(0x7EF311C7 - __float_as_int(ab.x)); r.y = __int_as_float(0x7EF311C7 - __float_as_int(ab.y));
+  const float2 nab = make_float2(-ab.x, -ab.y);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) r = __ffma2_rn(r, __ffma2_rn(nab, r, one), r);
+#else
   r.x = rcp_approx(ab.x); r.y = rcp_approx(ab.y);
+#endif
   const float2 z = __fmul2_rn(r, b);                                                          // rnn.py:290
   const float2 c = __ffma2_rn(__fmul2_rn(r, a), make_float2(2.0f, 2.0f), make_float2(-1.0f, -1.0f));   // rnn.py:292
   return __ffma2_rn(z, __ffma2_rn(k.msz, c, h), __fmul2_rn(k.szn, c));                        // rnn.py:294-295
@@ -129,10 +153,14 @@ struct TlEpiCtx {
   unsigned char* hop;                 // h operand tile address of (sub-tile 0, k = unit, this thread's first row group), hi part
   float* out; uint32_t out_row, out_step;      // &out[first row of sub-tile 0][t = 0][unit]; element strides
   int rows_left, T, tr;               // rows_left: B - first row (sub-tile 0); tr: trace role
+  const CUtensorMap* omap; float* stage;       // TL_TMA_STORE: output map; this warp's staging tiles [sub-tile][16 rows][32 units] (lane = unit)
+  int o_unit0, o_row0, o_time_outer;           // box origin: first unit, first row of sub-tile 0
 };
 
-// Epilogue main loop of one warp: thread = hidden unit; rows [rh*16, rh*16 + 16) of sub-tile 0, then of sub-tile 1.
-template <bool HAS_OUT, bool MASKED, bool ONE_EX2>
+// Epilogue main loop of one warp: thread = hidden unit; columns [rh*16, rh*16 + VR) of sub-tile 0, then of sub-tile 1.
+// VR = valid rows per thread and sub-tile (the other 16 - VR columns are padding: zero x, zero h, never stored): a CTA holds
+// 4 VR batch rows, and the epilogue's share of the per-step chain shrinks with VR while the MMAs cost the same (fgrnn_tc.cu).
+template <int VR, bool HAS_OUT, bool MASKED, bool ONE_EX2>
 static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, const TlEpiConst& kc, float2 (&hst)[TL_NT][TL_RPT / 2]) {
   char* outp = reinterpret_cast<char*>(cx.out);
   const uint32_t row_bytes = cx.out_row * 4u;
@@ -152,6 +180,7 @@ static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, cons
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int p = g * 4 + q;
+          if (p >= VR / 2) { hi[q] = 0u; lo[q] = 0u; continue; }
           hst[s][p] = tl_gate_update2<ONE_EX2>(make_float2(v[2 * q], v[2 * q + 1]), hst[s][p], kc);
           const __half2 hh = __float22half2_rn(hst[s][p]);
           const float2 hf = __half22float2(hh);
@@ -162,23 +191,49 @@ static __device__ __forceinline__ void tl_epilogue_loop(const TlEpiCtx& cx, cons
         *reinterpret_cast<uint4*>(cx.hop + s * (2 * TL_H_TILE) + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(cx.hop + s * (2 * TL_H_TILE) + TL_H_TILE + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      fence_proxy_async_smem();                        // st.shared of the h tile -> visible to tcgen05.mma
+      if (HAS_OUT && TL_TMA_STORE) {
+        // h_t -> this warp's staging tile (lane = unit: 128 contiguous bytes per row, immediate offsets); the TMA unit ships
+        // the 16 x 32 box after the fence below and clips rows past the batch end
+        float* st = cx.stage + s * (TL_STAGE_TILE / 4) + (threadIdx.x & 31);
+#pragma unroll
+        for (int q = 0; q < VR / 2; ++q) { st[(2 * q) * 32] = hst[s][q].x; st[(2 * q + 1) * 32] = hst[s][q].y; }
+      }
+      fence_proxy_async_smem();                        // st.shared of the h tile (and the staging tile) -> visible to the async proxy
       tc_fence_before();                               // tcgen05.ld of D2 done before stage 1 of the next step overwrites it
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(cx.bar_hready + 8 * s);
       if (cx.tr == 1) TL_TRACE(t, s, 7);
       if (cx.tr == 2) TL_TRACE(t, s, 10);
-      if (HAS_OUT) {
-        char* o = outp + (uint32_t)(s * TL_NS) * row_bytes;
+      if (HAS_OUT && TL_TMA_STORE) {
+        if ((threadIdx.x & 31) == 0) {
+          const uint32_t src = smem_u32(cx.stage + s * (TL_STAGE_TILE / 4));
+          const int row = cx.o_row0 + s * 2 * VR;
+          if (cx.o_time_outer)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(reinterpret_cast<uint64_t>(cx.omap)), "r"(cx.o_unit0), "r"(row), "r"(t), "r"(src) : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(reinterpret_cast<uint64_t>(cx.omap)), "r"(cx.o_unit0), "r"(t), "r"(row), "r"(src) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // the other sub-tile's store may stay in flight; the one issued a step ago from the tile that is written next is read out
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+      } else if (HAS_OUT) {
+        char* o = outp + (uint32_t)(s * 2 * VR) * row_bytes;
 #pragma unroll
-        for (int q = 0; q < TL_RPT / 2; ++q) {
-          if (!MASKED || s * TL_NS + 2 * q < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q) * row_bytes) = hst[s][q].x;
-          if (!MASKED || s * TL_NS + 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q + 1) * row_bytes) = hst[s][q].y;
+        for (int q = 0; q < VR / 2; ++q) {
+          if (!MASKED || s * 2 * VR + 2 * q < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q) * row_bytes) = hst[s][q].x;
+          if (!MASKED || s * 2 * VR + 2 * q + 1 < cx.rows_left) *reinterpret_cast<float*>(o + (uint32_t)(2 * q + 1) * row_bytes) = hst[s][q].y;
         }
       }
       if (cx.tr == 1) TL_TRACE(t, s, 8);
     }
-    if (HAS_OUT) outp += (size_t)cx.out_step * 4u;
+    if (HAS_OUT && !TL_TMA_STORE) outp += (size_t)cx.out_step * 4u;
+  }
+  if (HAS_OUT && TL_TMA_STORE) {
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory stays valid until the stores are done
+    __syncwarp();
   }
 }
 
@@ -204,7 +259,9 @@ static __device__ __forceinline__ void tl_issue_stage1(uint32_t acc, uint64_t dH
   }
 }
 
-__global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs ta, const __grid_constant__ CUtensorMap xmap) {
+template <int VR>
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs ta, const __grid_constant__ CUtensorMap xmap,
+                                                                 const __grid_constant__ CUtensorMap omap) {
   extern __shared__ __align__(128) unsigned char sm[];
   const FwdArgs& a = ta.f;
   const Dims d = a.d;
@@ -215,11 +272,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sm + L.misc);
   float* red_s = reinterpret_cast<float*>(sm + L.misc + 16);            // [3][16] reduction scratch, [48] = 2^-S1 for the hop warps
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int row0 = blockIdx.x * TL_ROWS;
+  const int row0 = blockIdx.x * (4 * VR);
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   // per sub-tile: HREADY (h_{t-1} tile written, D2 drained) | D1FULL | SREADY (s tile written, D1 drained) | DFULL
   const int B_HREADY = 0, B_D1FULL = 2, B_SREADY = 4, B_DFULL = 6, B_XFULL = 8, B_XEMPTY = 12, B_RAWFULL = 16;
-  constexpr int W_HOP0 = TL_EPI_WARPS, W_CONV0 = W_HOP0 + TL_HOP_WARPS, W_MMA = W_CONV0 + TL_CONV_WARPS;
+  // TL_HOP_HALVES == 1: warps 16..18 hop, 19..20 x path; == 2: warps 16..23, (warp & 3) < 3 hop, == 3 x path
+  constexpr int W_AUX0 = TL_EPI_WARPS, W_MMA = W_AUX0 + TL_HOP_WARPS + TL_CONV_WARPS;
+  const bool x_warp = warp >= W_AUX0 && warp < W_MMA && (TL_HOP_HALVES == 2 ? (warp & 3) == 3 : warp >= W_AUX0 + 3);
 
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_base_s), 512);
   if (tid == 0) {
@@ -293,13 +352,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       __syncwarp();
       if (role == 0) TL_TRACE(t, s, 3);
     }
-  } else if (warp >= W_CONV0) {
+  } else if (x_warp) {
     // =========================== x path: TMA -> fp16 hi/lo split -> K-major operand tiles =========================
     // converter warp cw owns sub-tile cw: 32 rows, one TMA box per step, a private raw ring
-    const int cw = warp - W_CONV0;
-    const uint32_t raw_bytes = (uint32_t)L.raw_stage_bytes;
+    const int cw = TL_HOP_HALVES == 2 ? (warp - W_AUX0) >> 2 : warp - (W_AUX0 + 3);
+    const uint32_t raw_bytes = (uint32_t)(2 * VR * I * esz);              // one TMA box: the sub-tile's 2 VR rows
     unsigned char* raw_base = sm + L.raw + cw * TL_RAW_STAGES * L.raw_stage_bytes;
-    const int my_row0 = row0 + cw * TL_CONV_ROWS;
+    const int my_row0 = row0 + cw * 2 * VR;
     auto issue_tma = [&](int t) {
       const int st = t % TL_RAW_STAGES;
       const uint32_t fb = bar(B_RAWFULL + cw * TL_RAW_STAGES + st);
@@ -318,10 +377,10 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int e = it * 32 + lane;
-      const int row = e / nch, ch = e - row * nch;
+      const int row = e / nch, ch = e - row * nch;      // row = column of the sub-tile: batch row (row >> 4) * VR + (row & 15) of it
       live[it] = e < ntask;
-      pad[it] = ch * 8 >= I;
-      src_off[it] = (uint32_t)(row * I * esz + ch * 8 * esz);
+      pad[it] = ch * 8 >= I || (row & 15) >= VR;
+      src_off[it] = (uint32_t)(((row >> 4) * VR + (row & 15)) * I * esz + ch * 8 * esz);
       dst_off[it] = (uint32_t)((cw * 2) * L.x_tile_bytes + (row >> 3) * (nch * 128) + ch * 128 + (row & 7) * 16);
     }
     const uint32_t xbuf_bytes = (uint32_t)(TL_NT * 2 * L.x_tile_bytes);
@@ -365,10 +424,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       }
       __syncwarp();
     }
-  } else if (warp >= W_HOP0) {
+  } else if (warp >= W_AUX0) {
     // =========================== hop: D1 (rank rows) -> fp16 hi/lo B operand of stage 2 ============================
-    // warp 16 + q reads lane quadrant q: lanes 0..15 = the main rows of 16 ranks, lanes 16..31 = their correction rows
-    const int quad = warp - W_HOP0;                    // == warp & 3: the TMEM lane quadrant this warp may access
+    // a hop warp reads lane quadrant q = warp & 3 (lanes 0..15 = the main rows of 16 ranks, lanes 16..31 = their correction
+    // rows) for one 16-row half of the sub-tile
+    const int quad = warp & 3;                         // the TMEM lane quadrant this warp may access
+    const int half0 = TL_HOP_HALVES == 2 ? (warp - W_AUX0) >> 2 : 0;      // first 16-row half (columns of D1) of this warp
     const int k = quad * 16 + (lane & 15);             // k index of the stage-2 operand: U1 ranks 0..31, then W1 ranks
     const int half_lane = lane >> 4;                   // which 8 of a half's 16 batch rows this lane converts and stores
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -381,10 +442,10 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
       for (int s = 0; s < TL_NT; ++s) {
         mbar_wait(bar(B_D1FULL + s), t & 1);
         tc_fence_after();
-        if (quad == 0) TL_TRACE(t, s, 4);
+        if (quad == 0 && half0 == 0) TL_TRACE(t, s, 4);
         const uint32_t d1 = tmem + lane_base + TLM_ACC + s * 64;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = half0; half < half0 + 2 / TL_HOP_HALVES; ++half) {
           float vx[16], vy[16];
           tmem_ld16(d1 + half * 16, vx);
           tmem_ld16(d1 + TL_NS + half * 16, vy);
@@ -407,7 +468,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_SREADY + s));
-        if (quad == 0) TL_TRACE(t, s, 5);
+        if (quad == 0 && half0 == 0) TL_TRACE(t, s, 5);
       }
     }
   } else {
@@ -528,7 +589,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     // ---- state: h[row][gu] for rows [rh*16, rh*16 + 16) of both sub-tiles; h_{-1} operand tiles
     float2 hst[TL_NT][TL_RPT / 2];
     unsigned char* hop = sm + L.h_op + (gu >> 3) * ((TL_NS >> 3) * 128) + (rh * 2) * 128 + (gu & 7) * 16;
-    const int first_row = row0 + rh * TL_RPT;          // of sub-tile 0; sub-tile 1: + TL_NS
+    const int first_row = row0 + rh * VR;              // of sub-tile 0; sub-tile 1: + 2 VR
 #pragma unroll
     for (int s = 0; s < TL_NT; ++s) {
 #pragma unroll
@@ -536,9 +597,10 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int row = first_row + s * TL_NS + g * 8 + 2 * q;
-          const float v0 = (a.h0 && row < d.B) ? __ldg(a.h0 + (size_t)row * TL_H + gu) : 0.f;
-          const float v1 = (a.h0 && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TL_H + gu) : 0.f;
+          const int row = first_row + s * 2 * VR + g * 8 + 2 * q;
+          const bool valid = g * 8 + 2 * q < VR;
+          const float v0 = (a.h0 && valid && row < d.B) ? __ldg(a.h0 + (size_t)row * TL_H + gu) : 0.f;
+          const float v1 = (a.h0 && valid && row + 1 < d.B) ? __ldg(a.h0 + (size_t)(row + 1) * TL_H + gu) : 0.f;
           hst[s][g * 4 + q] = make_float2(v0, v1);
           split2(v0, v1, 1.0f, hi[q], lo[q]);
         }
@@ -560,24 +622,26 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_lr_fwd_kernel(const TlArgs t
     cx.out_row = (uint32_t)a.osb; cx.out_step = (uint32_t)a.ost;
     cx.rows_left = d.B - first_row; cx.T = d.T;
     cx.tr = ew == 0 ? 1 : (ew == 15 ? 2 : 0);
-    const bool masked = row0 + TL_ROWS > d.B;
+    cx.omap = &omap; cx.stage = reinterpret_cast<float*>(sm + L.stage) + ew * TL_NT * (TL_STAGE_TILE / 4);
+    cx.o_unit0 = m * 128 + quad * 32; cx.o_row0 = first_row; cx.o_time_outer = ta.o_time_outer;
+    const bool masked = !TL_TMA_STORE && row0 + 4 * VR > d.B;      // the TMA unit clips its boxes at the batch end
     const int variant = (one_ex2 ? 4 : 0) | (a.out ? 2 : 0) | (masked ? 1 : 0);
     switch (variant) {
-      case 0: tl_epilogue_loop<false, false, false>(cx, kc, hst); break;
-      case 1: tl_epilogue_loop<false, true, false>(cx, kc, hst); break;
-      case 2: tl_epilogue_loop<true, false, false>(cx, kc, hst); break;
-      case 3: tl_epilogue_loop<true, true, false>(cx, kc, hst); break;
-      case 4: tl_epilogue_loop<false, false, true>(cx, kc, hst); break;
-      case 5: tl_epilogue_loop<false, true, true>(cx, kc, hst); break;
-      case 6: tl_epilogue_loop<true, false, true>(cx, kc, hst); break;
-      default: tl_epilogue_loop<true, true, true>(cx, kc, hst); break;
+      case 0: tl_epilogue_loop<VR, false, false, false>(cx, kc, hst); break;
+      case 1: tl_epilogue_loop<VR, false, true, false>(cx, kc, hst); break;
+      case 2: tl_epilogue_loop<VR, true, false, false>(cx, kc, hst); break;
+      case 3: tl_epilogue_loop<VR, true, true, false>(cx, kc, hst); break;
+      case 4: tl_epilogue_loop<VR, false, false, true>(cx, kc, hst); break;
+      case 5: tl_epilogue_loop<VR, false, true, true>(cx, kc, hst); break;
+      case 6: tl_epilogue_loop<VR, true, false, true>(cx, kc, hst); break;
+      default: tl_epilogue_loop<VR, true, true, true>(cx, kc, hst); break;
     }
     if (a.h_last) {
 #pragma unroll
       for (int s = 0; s < TL_NT; ++s) {
 #pragma unroll
-        for (int j = 0; j < TL_RPT; ++j) {
-          const int row = first_row + s * TL_NS + j;
+        for (int j = 0; j < VR; ++j) {
+          const int row = first_row + s * 2 * VR + j;
           if (row < d.B) a.h_last[(size_t)row * TL_H + gu] = (j & 1) ? hst[s][j >> 1].y : hst[s][j >> 1].x;
         }
       }
@@ -596,22 +660,47 @@ bool tc_lr_supports(const Dims& d) {
          d.gate_nl == FGRNN_NL_SIGMOID && d.update_nl == FGRNN_NL_TANH;
 }
 
-int launch_tc_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
+template <int VR>
+static int launch_tc_lr_fwd_vr(const FwdArgs& a, cudaStream_t stream) {
   const Dims& d = a.d;
-  if (d.B <= 0 || d.T <= 0) return FGRNN_OK;
   TlArgs ta{};
   ta.f = a;
   ta.KI = (d.I + 15) & ~15;
   const int esz = d.x_dtype == FGRNN_BF16 ? 2 : 4;
   CUtensorMap map;
-  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, TL_CONV_ROWS, &ta.x_time_outer);
+  const int rc = make_row_tile_map(&map, a.x, d.x_dtype == FGRNN_BF16, d.I, d.B, d.T, a.xsb, a.xst, 2 * VR, &ta.x_time_outer);
   if (rc) return rc;
+  CUtensorMap omap = map;                              // a valid descriptor even when there is no output tensor
+  if (a.out && TL_TMA_STORE) {
+    const int rc2 = make_row_tile_map(&omap, a.out, false, TL_H, d.B, d.T, a.osb, a.ost, VR, &ta.o_time_outer, 32);
+    if (rc2) return rc2;
+  }
   const TlSmem L = tl_smem_layout(d.I, ta.KI, esz);
-  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_lr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  const unsigned grid = (unsigned)((d.B + TL_ROWS - 1) / TL_ROWS);
-  tc_lr_fwd_kernel<<<grid, TL_THREADS, L.total, stream>>>(ta, map);
+  FGRNN_CUDA_TRY(cudaFuncSetAttribute(tc_lr_fwd_kernel<VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const unsigned grid = (unsigned)((d.B + 4 * VR - 1) / (4 * VR));
+  tc_lr_fwd_kernel<VR><<<grid, TL_THREADS, L.total, stream>>>(ta, map, omap);
   FGRNN_LAUNCH_CHECK("tc_lr_fwd_kernel");
   return FGRNN_OK;
+}
+
+// Valid rows per epilogue thread.  All CTAs take the same time, so a launch lasts rounds x chain with rounds = ceil(CTAs / 148);
+// the model below (chain ~ 3630 + 132 VR cycles per step: tools/trace_lowrank.py, 5750 at VR = 16 of which the epilogue 2120) only
+// ranks the candidates.  32768 rows: 512 CTAs of 64 rows are 3.46 rounds and take 4; 586 CTAs of 56 rows are 3.96 and take 4
+// shorter ones -- measured 1.126 -> 1.103 ms (same box, A/B).  FGRNN_TC_VR=16|14|12 overrides.
+int launch_tc_lr_fwd(const FwdArgs& a, cudaStream_t stream) {
+  if (a.d.B <= 0 || a.d.T <= 0) return FGRNN_OK;
+  int vr = tuning(TUNE_TC_VR);
+  if (vr != 16 && vr != 14 && vr != 12) {
+    double best = 0.0;
+    for (int cand = 16; cand >= 12; cand -= 2) {
+      const int ctas = (a.d.B + 4 * cand - 1) / (4 * cand);
+      const double cost = (double)((ctas + 147) / 148) * (3630.0 + 132.0 * cand);
+      if (cand == 16 || cost < best * 0.98) { best = cost; vr = cand; }
+    }
+  }
+  if (vr == 14) return launch_tc_lr_fwd_vr<14>(a, stream);
+  if (vr == 12) return launch_tc_lr_fwd_vr<12>(a, stream);
+  return launch_tc_lr_fwd_vr<16>(a, stream);
 }
 
 }  // namespace fgrnn

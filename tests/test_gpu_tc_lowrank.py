@@ -55,6 +55,26 @@ def test_tc_lowrank_forward_vs_oracle_and_ffma(B, T, I, wR, uR, layout, bf, h0, 
     assert torch.equal(last, out[:, -1] if bf else out[-1])
 
 
+@pytest.mark.parametrize("vr", ["14", "12"])
+def test_tc_lowrank_valid_rows_per_thread_is_bit_identical(tuning, vr):
+    """56- and 48-row CTAs (FGRNN_TC_VR = 14 / 12 valid rows per epilogue thread and sub-tile, the rest of the 2 x 32 MMA
+    columns padding) against the 64-row CTAs: same bits, ragged and multi-CTA batches, both layouts, bf16 input, h0."""
+    from kws_b200 import engine
+    for (B, T, I, wR, uR, layout, bf, h0, xbf16) in [(64, 3, 32, 16, 32, "IH", True, True, False), (150, 12, 32, 16, 32, "IH", True, True, False),
+                                                      (57, 7, 24, 12, 20, "HI", False, True, False), (33, 5, 32, 16, 32, "IH", True, False, True),
+                                                      (2000, 4, 32, 16, 32, "IH", True, False, False)]:
+        p, params, xg, h0g, ref = _case(B, T, I, wR, uR, layout, bf, h0, xbf16, seed=7 + B)
+        kw = dict(layout=layout, batch_first=bf, want_last=True)
+        tuning("FGRNN_TC_VR", "16")
+        a = engine.forward(xg, params, h0g, **kw)
+        tuning("FGRNN_TC_VR", vr)
+        b = engine.forward(xg, params, h0g, **kw)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a[0]).all()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]), (vr, B)
+        assert state_ratio(b[0], ref) <= 1.0
+
+
 def test_tc_lowrank_last_state_only_and_chunked_carry():
     """want_states=False writes no [B,T,H] at all; two chunks with state carry == one long call, bit for bit."""
     from kws_b200 import engine

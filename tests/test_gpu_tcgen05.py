@@ -96,6 +96,38 @@ def test_tcgen05_alternating_epilogue_is_bit_identical_to_the_split_one(tuning):
             assert state_ratio(a[0], ref) <= 1.0
 
 
+@pytest.mark.parametrize("ns,vr", [("32", "14")])
+def test_tcgen05_valid_rows_per_thread_is_bit_identical(tuning, ns, vr):
+    """2 x 32-row sub-tiles with 14 VALID rows per epilogue thread (56-row CTAs, FGRNN_TC_VR=14, opt-in) compute the very bits of the 64-row CTAs: a batch row is an independent column of the MMA.
+    Ragged and multi-CTA batches, saved gates, h0, both layouts, time-major output, bf16 input."""
+    from kws_b200 import _lib, engine
+    tuning("FGRNN_TC_NS", ns)
+    tuning("FGRNN_TC_NT", "2")
+    cases = [(64, 5, 32, False, False, True, False), (77, 9, 32, True, True, True, False), (300, 17, 16, True, False, False, False),
+             (57, 4, 24, False, True, True, True), (8192, 6, 32, False, True, True, False), (4099, 3, 32, True, False, True, False)]
+    for (B, T, I, save, h0_given, bf, xbf16) in cases:
+        torch.manual_seed(B + T)
+        p = O.init_params(I, 128)
+        params = {k: v.to(dev()).contiguous() for k, v in p.tensors().items()}
+        x = torch.randn(B, T, I, device=dev()) if bf else torch.randn(T, B, I, device=dev())
+        if xbf16:
+            x = x.bfloat16()
+        h0 = 0.5 * torch.randn(B, 128, device=dev()) if h0_given else None
+        kw = dict(layout="IH", batch_first=bf, want_last=True, save_for_backward=save, force_path=_lib.PATH_TCGEN05)
+        tuning("FGRNN_TC_VR", "16" if ns == "32" else "8")
+        a = engine.forward(x, params, h0, **kw)
+        tuning("FGRNN_TC_VR", vr)
+        b = engine.forward(x, params, h0, **kw)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a[0]).all()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]), (vr, B)
+        if save:
+            assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), (vr, B)
+        if B <= 300:
+            ref = O.unroll(x.float().cpu(), p, None if h0 is None else h0.cpu().unsqueeze(0), bf)
+            assert state_ratio(b[0], ref) <= 1.0
+
+
 def test_tcgen05_time_major_and_saved_gates():
     out, last, ref, z_s, c_s = _run(70, 6, 32, "HI", True, seed=3, batch_first=False, save=True)
     assert state_ratio(out, ref) <= 1.0
