@@ -214,7 +214,7 @@ def config_of(w, name, world):
             "T": w["T"], "input": w["I"], "hidden": w["H"], "wRank": w["wR"], "uRank": w["uR"], "x_dtype": w["x"],
             "layout": "(T,B,F) contiguous" if train else "(B,T,F) contiguous",
             "l2": "inputs+outputs per step = %.0f MB > 126 MB L2, no flush needed" % ((algorithmic_bytes_per_seq(w) * w["B"]) / 1e6),
-            "parallelism": "batch-sharded x%d%s" % (world, ", NCCL grad all-reduce" if train else ", no collective")}
+            "parallelism": "batch-sharded x%d%s" % (world, ", gradient all-reduce" if train else ", no collective")}
 
 
 class CpuReference:
@@ -382,6 +382,7 @@ class Bench:
         out = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         plan = engine.forward_plan(x, params, None, layout=args.layout, batch_first=True, force_path=self.force)
         graphed, cap = False, None
+        self.collective = None
 
         if train:
             from kws_b200 import graphs, rnn as krnn, train_step
@@ -394,20 +395,24 @@ class Bench:
             x_tm = x.transpose(0, 1).contiguous()
             labels = torch.randint(0, 13, (B,), device=dev)
             fused = args.train_api == "fused"
+            if world > 1 and self.cap_group is None and not args.no_graph:
+                # the captured collective gets a communicator of its own: the eager barrier / timing collectives of the harness
+                # stay on the default one (a collective captured next to eager collectives on the SAME communicator hung in round 1)
+                self.cap_group = self.dist.new_group(backend="nccl")
             if fused:
-                # kws_b200.train_step: recurrence, fused head+loss kernel, BPTT from the last state's gradient, flat SGD
-                stepper = train_step.LastStateTrainStep(layer, head, 1e-3, data_parallel=False)
-                stepper.world = world
+                # kws_b200.train_step: recurrence, fused head+loss kernel, BPTT from the last state's gradient, then (one GPU) flat
+                # SGD or (data parallel) the fused all-reduce + SGD kernel over NVLink peer memory; --collective nccl = ncclAllReduce + SGD
+                stepper = train_step.LastStateTrainStep(layer, head, 1e-3, group=self.cap_group, data_parallel=world > 1,
+                                                        collective=args.collective)
+                self.collective = stepper.collective
 
                 def step_compute():
                     stepper.compute(x_tm, labels)
 
                 def step():
                     step_compute()
-                    if world > 1:
-                        self.dist.all_reduce(stepper.flat_grads, group=self.cap_group)     # SUM; 1/world folded into the SGD kernel
-                    train_step.sgd_flat(stepper.flat_params, stepper.flat_grads, stepper.lr, 1.0 / world)
-                opt_step = lambda: train_step.sgd_flat(stepper.flat_params, stepper.flat_grads, stepper.lr, 1.0 / world)   # noqa: E731
+                    stepper.update()
+                opt_step = stepper.update
             else:
                 # the module API through autograd, as the unchanged trainClassifier.py drives it
                 bucket = sharding.GradBucket(plist)
@@ -430,11 +435,6 @@ class Bench:
             run_step = step
             if not args.no_graph:
                 try:
-                    if world > 1 and self.cap_group is None:
-                        # the captured all-reduce gets a communicator of its own: the eager barrier / timing collectives of
-                        # the harness stay on the default one (a collective captured next to eager collectives on the SAME
-                        # communicator hung in round 1)
-                        self.cap_group = self.dist.new_group(backend="nccl")
                     for _ in range(max(warmup, 3)):
                         step()                        # also initialises the communicator outside of any capture
                     torch.cuda.synchronize(dev)
@@ -449,9 +449,9 @@ class Bench:
 
                         def run_step():
                             cap()
-                            if fused:
+                            if fused and stepper.peer is None:
                                 self.dist.all_reduce(stepper.flat_grads, group=self.cap_group)
-                            else:
+                            elif not fused:
                                 bucket.all_reduce_mean(group=self.cap_group)
                             cap_opt()
                         graphed = True
@@ -525,6 +525,11 @@ class Bench:
                "value": value, "unit": "sequences/s", "ms_per_step": ms_per_step, "rank_ms_per_step": rank_ms, "steps": steps,
                "kernel_path": plan, "cuda_graph": graphed, "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
                "config": dict(config_of(w, name, world), weight_layout=args.layout, kernel_path=plan, cuda_graph=graphed)}
+        if train:
+            # which collective ran the gradient exchange: "peer" = our fused all-reduce + SGD kernel over NVLink peer memory
+            rec["collective"] = self.collective if (args.train_api == "fused" and world > 1) else ("nccl" if world > 1 else "none")
+            if args.train_api == "fused" and stepper.peer is not None:
+                stepper.peer.check()                  # raises if a peer failed to arrive in any step
         if not full:
             del x, out, x_host
             torch.cuda.empty_cache()
@@ -597,6 +602,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="training workloads: time the eager step, not the CUDA graph")
     ap.add_argument("--train-api", default="fused", choices=["fused", "module"],
                     help="training workloads: kws_b200.train_step (default) or the module API through autograd")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="data-parallel training: fused all-reduce + SGD kernel over NVLink peer memory, or ncclAllReduce + SGD")
     ap.add_argument("--chunk-rows", type=int, default=1024, help="rows per pipeline chunk of the host-buffer API")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -636,6 +643,8 @@ def main():
                                                  "cuda_graph", "gpu_launches", "clocks")}
                 extra[name]["roofline"] = {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms")}
                 extra[name]["workload"] = r["config"]["workload"]
+                if "collective" in r:
+                    extra[name]["collective"] = r["collective"]
             except Exception as e:                   # noqa: BLE001 -- an extra must never take the headline down
                 extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -652,7 +661,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(w, args.workload, world),
             "impl_detail": {"weight_layout": args.layout, "kernel_path": rec["kernel_path"], "cuda_graph": rec["cuda_graph"],
-                            "numa": numa, "e2e_chunk_rows": args.chunk_rows},
+                            "numa": numa, "e2e_chunk_rows": args.chunk_rows, "collective": rec.get("collective")},
             "roofline": rec["roofline"], "cpu_baseline": cpu, "e2e": rec.get("e2e"), "gpu_launches": rec["gpu_launches"],
             "clocks": rec["clocks"], "extra": extra,
         }

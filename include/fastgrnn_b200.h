@@ -201,6 +201,40 @@ FGRNN_API int fgrnn_head_nll(const float* h, int64_t h_stride, const float* W, c
    bucket holds the all-reduced SUM of the ranks' gradients. */
 FGRNN_API int fgrnn_sgd_flat(float* params, const float* grads, int64_t n, float lr, float grad_scale, int32_t device, void* stream);
 
+/* Data-parallel training step: gradient all-reduce FUSED with the SGD update over NVLink peer memory -- what replaces
+   `all_reduce(flat bucket)` followed by `optimizer.step()` (trainClassifier.py:239-240 under one process per GPU; the north
+   star's data-parallel configuration).  Every rank owns a region obtained from fgrnn_peer_alloc (zero-filled), sends its
+   64-byte CUDA IPC handle to its peers (any transport: torch.distributed's object collectives, MPI, a file) and opens theirs
+   with fgrnn_peer_open.  Region layout: [gradient bucket, n floats, padded to a multiple of 256 bytes][receive area,
+   fgrnn_peer_recv_bytes(n, world) bytes].  Ranks must be in ONE node with P2P access (NVLink / NVSwitch), world <= 8.
+     fgrnn_sgd_allreduce_peer: every rank pushes its bucket into the peers' receive areas (16-byte lines that carry the step
+                               counter as their flag), then sum = bucket of rank 0 + rank 1 + ... (rank order, identical bits
+                               on every rank); params -= lr * (grad_scale * sum); reduced (optional) = sum.
+   Every rank must call it the same number of times with the same n (it is a collective); the launch is asynchronous on
+   `stream` and may be captured in a CUDA graph (its step counters live in `state`: fgrnn_peer_state_bytes() of ZEROED device
+   memory, private to the rank).  After a synchronisation, state[32] != 0 means a peer's lines did not arrive within 4 s. */
+#define FGRNN_PEER_MAX_RANKS 8
+#define FGRNN_PEER_HANDLE_BYTES 64
+typedef struct FgrnnPeerStep {
+  int32_t abi_version;       /* FGRNN_ABI_VERSION */
+  int32_t device;
+  int32_t world, rank;
+  float* params;             /* [n] this rank's flat parameters (updated) */
+  float* reduced;            /* [n] or NULL: the summed gradients (what p.grad holds after the all-reduce) */
+  const float* bucket;       /* [n] this rank's gradients (the start of its own region) */
+  void* recv[FGRNN_PEER_MAX_RANKS];        /* every rank's receive area as mapped in THIS process; [rank] = the local one */
+  int32_t* state;            /* local, fgrnn_peer_state_bytes(), zero before the first call */
+  int64_t n;
+  float lr, grad_scale;      /* grad_scale = 1 / world for the mean over ranks */
+} FgrnnPeerStep;
+FGRNN_API size_t fgrnn_peer_recv_bytes(int64_t n, int32_t world);
+FGRNN_API size_t fgrnn_peer_state_bytes(void);
+FGRNN_API int fgrnn_peer_alloc(size_t bytes, int32_t device, void** ptr, unsigned char* handle /* [FGRNN_PEER_HANDLE_BYTES] out */);
+FGRNN_API int fgrnn_peer_open(const unsigned char* handle, int32_t device, void** ptr);
+FGRNN_API int fgrnn_peer_close(void* ptr, int32_t device);
+FGRNN_API int fgrnn_peer_free(void* ptr, int32_t device);
+FGRNN_API int fgrnn_sgd_allreduce_peer(const FgrnnPeerStep* step, void* stream);
+
 /* Tuning / test override of the launchers' tile configuration.  Keys are the names of the environment variables that set
    the same values at process start (FGRNN_TC_NS, FGRNN_TC_NT, FGRNN_TC_BR_NS, FGRNN_TC_WIDE, FGRNN_FAST_NL,
    FGRNN_SMEM_CFG); the environment is read once, not on the launch path.  value NULL or "" clears the override. */

@@ -70,6 +70,18 @@ class FgrnnBackward(C.Structure):
     ]
 
 
+PEER_MAX_RANKS, PEER_HANDLE_BYTES = 8, 64
+
+
+class FgrnnPeerStep(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
+        ("params", _fp), ("reduced", _fp),
+        ("bucket", _fp), ("recv", _fp * PEER_MAX_RANKS),
+        ("state", _fp), ("n", C.c_int64), ("lr", C.c_float), ("grad_scale", C.c_float),
+    ]
+
+
 # every symbol include/fastgrnn_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "fgrnn_forward_workspace_bytes": (C.c_size_t, [C.POINTER(FgrnnForward)]),
@@ -88,6 +100,13 @@ SYMBOLS = {
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_void_p]),
     "fgrnn_sgd_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+    "fgrnn_peer_recv_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "fgrnn_peer_state_bytes": (C.c_size_t, []),
+    "fgrnn_peer_alloc": (C.c_int, [C.c_size_t, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p]),
+    "fgrnn_peer_open": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "fgrnn_peer_close": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fgrnn_peer_free": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fgrnn_sgd_allreduce_peer": (C.c_int, [C.POINTER(FgrnnPeerStep), C.c_void_p]),
     "fgrnn_debug_poison_onchip": (C.c_int, [C.c_int, C.c_void_p]),
     "fgrnn_debug_set_tuning": (C.c_int, [C.c_char_p, C.c_char_p]),
     "fgrnn_ingest_bft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -12,6 +12,9 @@ forward and in backward up to the parameter-gradient sum; time is strictly seque
   latency-bound; it is issued on the compute stream right after the reduce kernel that
   writes the bucket.
 
+* training, one node -- ``PeerReducer``: the all-reduce FUSED with the SGD step in one kernel of ours that loads the
+  peers' buckets over NVLink peer memory (``csrc/fgrnn_peer.cu``); NCCL stays the fallback (several nodes, no P2P).
+
 The reference has no distributed code at all; this is new work behind the same module API.
 """
 from __future__ import annotations
@@ -123,6 +126,124 @@ class _MeanWork:
 
     def is_completed(self) -> bool:
         return self._done or self._work.is_completed()
+
+
+class _RawDeviceArray:
+    """A float32 view of raw device memory for ``torch.as_tensor`` (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, numel: int):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerReducer:
+    """The gradient bucket of one rank in NVLink peer memory, and the fused all-reduce + SGD step over it
+    (``fgrnn_sgd_allreduce_peer``, include/fastgrnn_b200.h).
+
+    ``bucket`` is where the backward pass writes this rank's gradients (a float32 tensor view of a ``fgrnn_peer_alloc``
+    region whose CUDA IPC handle every other rank has opened).  ``step(params, lr, reduced=...)`` pushes it into every
+    peer's receive area, sums all ranks' gradients in rank order and applies ``params -= lr / world * sum`` in one launch
+    -- every rank computes the very same bits, there is no NCCL call on the path, and the launch can be captured in a
+    CUDA graph.
+
+    Construction is a collective over ``group`` (handles travel through ``all_gather_object``).  All ranks must be
+    processes of ONE node whose GPUs have P2P access; otherwise construction raises and the caller keeps NCCL."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import ctypes as C
+        from . import _lib
+        if device.type != "cuda":
+            raise RuntimeError("PeerReducer needs a CUDA device")
+        lib = _lib.load()
+        self.group, self.device, self.numel = group, device, int(numel)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.PEER_MAX_RANKS:
+            raise RuntimeError("PeerReducer: %d ranks, at most %d (one NVSwitch node)" % (self.world, _lib.PEER_MAX_RANKS))
+        self._index = device.index if device.index is not None else torch.cuda.current_device()
+        self._grad_bytes = (4 * self.numel + 255) // 256 * 256
+        total = self._grad_bytes + int(lib.fgrnn_peer_recv_bytes(self.numel, self.world))
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(lib.fgrnn_peer_alloc(total, self._index, C.byref(ptr), handle), "peer_alloc")
+        self._local = int(ptr.value)
+        self._opened = []
+        # every rank must learn whether ALL ranks could map ALL regions before anyone relies on the fused step
+        mine = (bytes(handle.raw), self._index, _node_id())
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine, group=group)
+        err = None
+        self.ptrs = [0] * self.world
+        try:
+            if len({info[2] for info in infos}) != 1:
+                raise RuntimeError("ranks are on different hosts")
+            for r, (hbytes, _, _) in enumerate(infos):
+                if r == self.rank:
+                    self.ptrs[r] = self._local
+                    continue
+                out = C.c_void_p()
+                _lib.check(lib.fgrnn_peer_open(hbytes, self._index, C.byref(out)), "peer_open(rank %d)" % r)
+                self.ptrs[r] = int(out.value)
+                self._opened.append(int(out.value))
+        except RuntimeError as e:             # noqa: PERF203
+            err = str(e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err, group=group)
+        bad = [(r, e) for r, e in enumerate(oks) if e is not None]
+        if bad:
+            self.close()
+            raise RuntimeError("PeerReducer: peer memory is not available (rank %d: %s)" % bad[0])
+        self.bucket = torch.as_tensor(_RawDeviceArray(self._local, self.numel), device=device)
+        self.state = torch.zeros(int(lib.fgrnn_peer_state_bytes()) // 4, dtype=torch.int32, device=device)
+        self.steps = 0
+        torch.cuda.synchronize(device)
+
+    def step(self, params: torch.Tensor, lr: float, reduced: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> None:
+        """``params -= lr / world * (sum over ranks of bucket)``; ``reduced`` (optional, [numel]) receives the sum."""
+        import ctypes as C
+        from . import _lib, engine
+        if params.dtype != torch.float32 or not params.is_contiguous() or params.numel() != self.numel:
+            raise RuntimeError("PeerReducer.step: params must be a contiguous float32 buffer of %d elements" % self.numel)
+        if reduced is not None and (reduced.dtype != torch.float32 or not reduced.is_contiguous() or reduced.numel() < self.numel):
+            raise RuntimeError("PeerReducer.step: reduced must be a contiguous float32 buffer of %d elements" % self.numel)
+        d = _lib.FgrnnPeerStep()
+        d.abi_version, d.device, d.world, d.rank = _lib.ABI_VERSION, self._index, self.world, self.rank
+        d.params = params.data_ptr()
+        d.reduced = reduced.data_ptr() if reduced is not None else None
+        d.bucket = self._local
+        for r in range(self.world):
+            d.recv[r] = self.ptrs[r] + self._grad_bytes
+        d.state = self.state.data_ptr()
+        d.n, d.lr, d.grad_scale = self.numel, float(lr), 1.0 / self.world
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().fgrnn_sgd_allreduce_peer(C.byref(d), engine._stream(self.device) if stream is None else stream),
+                       "sgd_allreduce_peer")
+        self.steps += 1
+
+    def check(self) -> None:
+        """After a synchronisation: raise if a peer failed to arrive in some step (the kernel gives up after 4 s)."""
+        flag = int(self.state[-1].item())
+        if flag:
+            raise RuntimeError("PeerReducer: the gradients of rank %d did not arrive in a fused all-reduce step" % (flag - 1))
+
+    def close(self) -> None:
+        from . import _lib
+        lib = _lib.load()
+        for p in self._opened:
+            lib.fgrnn_peer_close(p, self._index)
+        self._opened = []
+        if self._local:
+            self.bucket = None
+            lib.fgrnn_peer_free(self._local, self._index)
+            self._local = 0
+
+
+def _node_id() -> str:
+    import socket
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except OSError:
+        return socket.gethostname()
 
 
 def broadcast_parameters(params: Sequence[torch.Tensor], src: int = 0, group=None) -> None:

@@ -10,7 +10,9 @@ recurrence and a handful of optimizer launches.  Here the same arithmetic is
     2. head forward + loss + head backward, one kernel             ``fgrnn_head_nll``  -> loss, dW_head, db_head, dh_T
     3. BPTT from the LAST state's gradient only (``grad_t0=T-1``)  ``fgrnn_backward``  -> reverse recurrence,
        contraction, reduce; parameter gradients land in ONE flat bucket
-    4. (data parallel) one all-reduce of the bucket
+    4. + 5. (data parallel, one node) all-reduce FUSED with SGD    ``fgrnn_sgd_allreduce_peer`` -- one kernel that loads the
+       peers' buckets over NVLink peer memory, sums them in rank order and updates the parameters (csrc/fgrnn_peer.cu)
+    4. (data parallel, NCCL fallback) one all-reduce of the bucket
     5. SGD over the flat parameter buffer                          ``fgrnn_sgd_flat``
 
 with no autograd graph.  Parameters of the layer and the head are re-pointed at views of one flat buffer, so the
@@ -85,9 +87,13 @@ def sgd_flat(params: torch.Tensor, grads: torch.Tensor, lr: float, grad_scale: f
 class LastStateTrainStep:
     """``step(x, labels) -> loss`` for one FastGRNN layer (``kws_b200.rnn.FastGRNN``) followed by the
     ``hidden2keyword`` linear head, plain SGD.  ``group``: process group for data-parallel training (gradients of the
-    ranks' mean losses are averaged, i.e. the loss over the concatenated batch when the slices have equal size)."""
+    ranks' mean losses are averaged, i.e. the loss over the concatenated batch when the slices have equal size).
+    ``collective``: "peer" = the fused all-reduce + SGD kernel over NVLink peer memory (``sharding.PeerReducer``; raises if
+    the ranks cannot map each other's memory), "nccl" = ``dist.all_reduce`` + ``fgrnn_sgd_flat``, "auto" = peer when it can
+    be set up, else nccl (``self.collective`` tells which)."""
 
-    def __init__(self, layer, head: torch.nn.Linear, lr: float, group=None, data_parallel: Optional[bool] = None):
+    def __init__(self, layer, head: torch.nn.Linear, lr: float, group=None, data_parallel: Optional[bool] = None,
+                 collective: str = "auto"):
         if type(layer).__name__ != "FastGRNN" or getattr(layer, "_bidirectional", False):
             raise RuntimeError("LastStateTrainStep drives one unidirectional kws_b200.rnn.FastGRNN layer")
         cell = layer.cell
@@ -114,8 +120,6 @@ class LastStateTrainStep:
                 p.grad = self.flat_grads[off:off + p.numel()].view(p.shape)
                 off += p.numel()
         self.params = {k: getattr(cell, k).data for k in names}
-        self.dW_head = head.weight.grad
-        self.db_head = head.bias.grad
         H, Cn = head.weight.shape[1], head.weight.shape[0]
         self._head_ws = None
         self._H, self._C = H, Cn
@@ -124,6 +128,23 @@ class LastStateTrainStep:
             data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         if data_parallel:
             self.world = dist.get_world_size(group)
+        # where this rank's gradients are written: the flat bucket itself, or -- fused peer step -- a bucket in NVLink peer
+        # memory (flat_grads, i.e. every p.grad, then receives the all-reduced SUM from the same kernel that updates the parameters)
+        self.peer = None
+        self.collective = "none" if self.world == 1 else "nccl"
+        if collective not in ("auto", "peer", "nccl"):
+            raise ValueError("collective must be 'auto', 'peer' or 'nccl'")
+        if self.world > 1 and collective != "nccl":
+            from . import sharding
+            try:
+                self.peer = sharding.PeerReducer(total, dev, group)
+                self.collective = "peer"
+            except RuntimeError:
+                if collective == "peer":
+                    raise
+        self.bucket = self.peer.bucket if self.peer is not None else self.flat_grads
+        self.dW_head = self.bucket[self.n_cell:self.n_cell + head.weight.numel()].view(head.weight.shape)
+        self.db_head = self.bucket[self.n_cell + head.weight.numel():total].view(head.bias.shape)
 
     def compute(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """Forward, loss and every gradient (into ``flat_grads``); no collective, no update."""
@@ -140,10 +161,13 @@ class LastStateTrainStep:
         gh = dh.unsqueeze(1) if self.batch_first else dh.unsqueeze(0)
         engine.backward(gh, x, out, z_s, c_s, self.params, None, layout=self.layout, batch_first=self.batch_first,
                         gate_nl=self.gate_nl, update_nl=self.update_nl, need_dx=False, need_dh0=False,
-                        grad_bucket=self.flat_grads, grad_t0=T - 1)
+                        grad_bucket=self.bucket, grad_t0=T - 1)
         return loss
 
     def update(self) -> None:
+        if self.peer is not None:
+            self.peer.step(self.flat_params, self.lr, reduced=self.flat_grads)
+            return
         if self.world > 1:
             dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
         sgd_flat(self.flat_params, self.flat_grads, self.lr, 1.0 / self.world)

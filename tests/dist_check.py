@@ -10,6 +10,9 @@
 4. the keyword spotter's step on the last state (kws_b200.train_step.LastStateTrainStep: fused head + loss kernel, BPTT from
    the last state's gradient, ONE all-reduce of the flat bucket, flat SGD with the 1 / world folded in): two data-parallel
    steps leave every rank with the parameters of two single-GPU steps over the concatenated batch.
+5. the same step with the gradient exchange FUSED into the SGD kernel over NVLink peer memory (sharding.PeerReducer,
+   fgrnn_sgd_allreduce_peer): parameters after eager steps and after CUDA-graph replays of the whole step == the single-GPU
+   run within the tolerance, p.grad == the NCCL sum within rounding, and every rank holds the very same bits.
 Prints "DIST_CHECK ok" on rank 0; any mismatch raises."""
 import os
 import sys
@@ -103,8 +106,8 @@ def main():
     ref_step = train_step.LastStateTrainStep(l_ref, h_ref, 0.05, data_parallel=False)
     l_dp, h_dp = make_model()
     sharding.broadcast_parameters(list(l_dp.cell.parameters()) + list(h_dp.parameters()))
-    dp_step = train_step.LastStateTrainStep(l_dp, h_dp, 0.05, data_parallel=True)
-    assert dp_step.world == world
+    dp_step = train_step.LastStateTrainStep(l_dp, h_dp, 0.05, data_parallel=True, collective="nccl")
+    assert dp_step.world == world and dp_step.collective == "nccl"
     for xa in (x_all, x2_all):
         loss_ref = ref_step(xa, labels_all)
         loss_dp = dp_step(xa[:, b:e].contiguous(), labels_all[b:e].contiguous())
@@ -114,10 +117,47 @@ def main():
     torch.cuda.synchronize()
     worst_p = float(((dp_step.flat_params - ref_step.flat_params).abs() / (1e-6 + 1e-5 * ref_step.flat_params.abs())).max())
     assert worst_p <= 1.0, "rank %d: parameters after two data-parallel fused steps off by %.3f x (rtol 1e-5, atol 1e-6)" % (rank, worst_p)
+
+    # ---- 5. the gradient exchange fused into the SGD kernel over NVLink peer memory
+    l_ref2, h_ref2 = make_model()
+    ref2 = train_step.LastStateTrainStep(l_ref2, h_ref2, 0.05, data_parallel=False)
+    l_pp, h_pp = make_model()
+    sharding.broadcast_parameters(list(l_pp.cell.parameters()) + list(h_pp.parameters()))
+    pp_step = train_step.LastStateTrainStep(l_pp, h_pp, 0.05, data_parallel=True, collective="peer")
+    assert pp_step.collective == "peer" and pp_step.peer is not None
+    l_nc, h_nc = make_model()
+    sharding.broadcast_parameters(list(l_nc.cell.parameters()) + list(h_nc.parameters()))
+    nc_step = train_step.LastStateTrainStep(l_nc, h_nc, 0.05, data_parallel=True, collective="nccl")
+    xs2, ls2 = x2_all[:, b:e].contiguous(), labels_all[b:e].contiguous()
+    for xa in (x_all, x2_all):                         # two eager steps
+        ref2(xa, labels_all)
+        pp_step(xa[:, b:e].contiguous(), labels_all[b:e].contiguous())
+        nc_step(xa[:, b:e].contiguous(), labels_all[b:e].contiguous())
+    torch.cuda.synchronize()
+    pp_step.peer.check()
+    worst_g = float(((pp_step.flat_grads - nc_step.flat_grads).abs() / (1e-7 + 1e-5 * nc_step.flat_grads.abs())).max())
+    assert worst_g <= 1.0, "rank %d: peer-reduced gradient sum differs from the NCCL sum by %.3f x (rtol 1e-5)" % (rank, worst_g)
+    cap5 = graphs.CapturedStep(lambda: pp_step(xs2, ls2), warmup=1)      # the whole step incl. the peer exchange as ONE graph
+    torch.cuda.synchronize()
+    for _ in range(3):
+        cap5()
+    torch.cuda.synchronize()
+    pp_step.peer.check()
+    for _ in range(1 + 3):                             # the warm-up call of CapturedStep and three replays (capture itself runs nothing)
+        ref2(x2_all, labels_all)
+    torch.cuda.synchronize()
+    worst_pp = float(((pp_step.flat_params - ref2.flat_params).abs() / (1e-6 + 1e-5 * ref2.flat_params.abs())).max())
+    assert worst_pp <= 1.0, "rank %d: parameters after six peer-fused steps off by %.3f x (rtol 1e-5, atol 1e-6)" % (rank, worst_pp)
+    allp = [torch.empty_like(pp_step.flat_params) for _ in range(world)]
+    dist.all_gather(allp, pp_step.flat_params)
+    assert all(torch.equal(allp[0], q) for q in allp), "rank %d: the replicas' parameters are not bit-identical" % rank
+    del cap5
     dist.barrier(device_ids=[local])
     if rank == 0:
         print("DIST_CHECK ok: world %d, sharded inference bitwise, all-reduced gradients at %.3f of tolerance, captured step bitwise, "
-              "fused last-state step parameters at %.3f of (1e-5, 1e-6)" % (world, worst, worst_p), flush=True)
+              "fused last-state step parameters at %.3f of (1e-5, 1e-6); peer-memory all-reduce + SGD kernel: gradient sum at %.3f of "
+              "rtol 1e-5 against NCCL, parameters after 6 steps (3 through one CUDA graph) at %.3f, replicas bit-identical"
+              % (world, worst, worst_p, worst_g, worst_pp), flush=True)
     sys.stdout.flush()
     os._exit(0)                               # skip the process-group teardown: nothing left to do, and it must never hang a test
 

@@ -49,7 +49,8 @@ def test_struct_layout_matches_header(tmp_path):
     """Compile a C program against the real header and compare sizeof/offsetof with ctypes."""
     fields = {"FgrnnProblem": [f for f, _ in _lib.FgrnnProblem._fields_],
               "FgrnnForward": [f for f, _ in _lib.FgrnnForward._fields_],
-              "FgrnnBackward": [f for f, _ in _lib.FgrnnBackward._fields_]}
+              "FgrnnBackward": [f for f, _ in _lib.FgrnnBackward._fields_],
+              "FgrnnPeerStep": [f for f, _ in _lib.FgrnnPeerStep._fields_]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fastgrnn_b200.h"', 'int main(void){']
     for s, fs in fields.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
@@ -67,6 +68,27 @@ def test_struct_layout_matches_header(tmp_path):
         assert int(got[s]) == C.sizeof(cls), s
         for f in fields[s]:
             assert int(got["%s.%s" % (s, f)]) == getattr(cls, f).offset, (s, f)
+
+
+def test_peer_step_descriptor_validation(lib):
+    """fgrnn_sgd_allreduce_peer rejects a bad descriptor before it touches a device; the sizes of the flag / state areas are fixed."""
+    assert lib.fgrnn_peer_recv_bytes(21, 4) == 2 * 4 * 11 * 16 and lib.fgrnn_peer_recv_bytes(0, 4) == 0 and lib.fgrnn_peer_state_bytes() == 33 * 4
+    assert lib.fgrnn_sgd_allreduce_peer(None, None) == _lib.ERR_NULL
+    d = _lib.FgrnnPeerStep()
+    d.abi_version, d.world, d.rank, d.n = _lib.ABI_VERSION + 1, 2, 0, 16
+    assert lib.fgrnn_sgd_allreduce_peer(C.byref(d), None) == _lib.ERR_VERSION
+    d.abi_version = _lib.ABI_VERSION
+    for world, rank in [(0, 0), (9, 0), (2, 2), (2, -1)]:
+        d.world, d.rank = world, rank
+        assert lib.fgrnn_sgd_allreduce_peer(C.byref(d), None) == _lib.ERR_SHAPE
+    d.world, d.rank = 2, 1
+    assert lib.fgrnn_sgd_allreduce_peer(C.byref(d), None) == _lib.ERR_NULL           # params / state missing
+    d.params, d.state = 0x1000, 0x2000
+    assert lib.fgrnn_sgd_allreduce_peer(C.byref(d), None) == _lib.ERR_NULL           # bucket / receive areas missing
+    d.bucket = 0x3000
+    d.recv[0], d.recv[1] = 0x4000, 0x5008
+    assert lib.fgrnn_sgd_allreduce_peer(C.byref(d), None) == _lib.ERR_ALIGN
+    assert lib.fgrnn_peer_alloc(0, 0, None, None) == _lib.ERR_NULL
 
 
 def _fwd(**kw):
