@@ -162,30 +162,37 @@ class PeerReducer:
         self._index = device.index if device.index is not None else torch.cuda.current_device()
         self._grad_bytes = (4 * self.numel + 255) // 256 * 256
         total = self._grad_bytes + int(lib.fgrnn_peer_recv_bytes(self.numel, self.world))
+        # Construction is a collective: a rank that fails locally still takes part in both object all-gathers (carrying its
+        # error), so that every rank raises together and none is left waiting for the others
         ptr = C.c_void_p()
         handle = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
-        _lib.check(lib.fgrnn_peer_alloc(total, self._index, C.byref(ptr), handle), "peer_alloc")
-        self._local = int(ptr.value)
-        self._opened = []
-        # every rank must learn whether ALL ranks could map ALL regions before anyone relies on the fused step
-        mine = (bytes(handle.raw), self._index, _node_id())
-        infos = [None] * self.world
-        dist.all_gather_object(infos, mine, group=group)
+        self._local, self._opened, self.bucket = 0, [], None
         err = None
-        self.ptrs = [0] * self.world
         try:
-            if len({info[2] for info in infos}) != 1:
-                raise RuntimeError("ranks are on different hosts")
-            for r, (hbytes, _, _) in enumerate(infos):
-                if r == self.rank:
-                    self.ptrs[r] = self._local
-                    continue
-                out = C.c_void_p()
-                _lib.check(lib.fgrnn_peer_open(hbytes, self._index, C.byref(out)), "peer_open(rank %d)" % r)
-                self.ptrs[r] = int(out.value)
-                self._opened.append(int(out.value))
-        except RuntimeError as e:             # noqa: PERF203
+            _lib.check(lib.fgrnn_peer_alloc(total, self._index, C.byref(ptr), handle), "peer_alloc")
+            self._local = int(ptr.value)
+        except RuntimeError as e:
             err = str(e)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (bytes(handle.raw), self._index, _node_id(), err), group=group)
+        self.ptrs = [0] * self.world
+        if err is None:
+            try:
+                failed = [(r, info[3]) for r, info in enumerate(infos) if info[3] is not None]
+                if failed:
+                    raise RuntimeError("rank %d could not allocate its region: %s" % failed[0])
+                if len({info[2] for info in infos}) != 1:
+                    raise RuntimeError("ranks are on different hosts")
+                for r, info in enumerate(infos):
+                    if r == self.rank:
+                        self.ptrs[r] = self._local
+                        continue
+                    out = C.c_void_p()
+                    _lib.check(lib.fgrnn_peer_open(info[0], self._index, C.byref(out)), "peer_open(rank %d)" % r)
+                    self.ptrs[r] = int(out.value)
+                    self._opened.append(int(out.value))
+            except RuntimeError as e:
+                err = str(e)
         oks = [None] * self.world
         dist.all_gather_object(oks, err, group=group)
         bad = [(r, e) for r, e in enumerate(oks) if e is not None]

@@ -87,3 +87,24 @@ def _worker(rank, world, port, total_rows):
 @pytest.mark.parametrize("total_rows", [16, 17])
 def test_data_parallel_logic_world2_gloo(total_rows):
     mp.spawn(_worker, args=(2, _free_port(), total_rows), nprocs=2, join=True)
+
+
+def _peer_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # No GPU here: fgrnn_peer_alloc fails on every rank.  Construction is a collective, so each rank must carry its error
+        # through both object all-gathers and ALL ranks must raise the same RuntimeError -- nobody may be left waiting
+        with pytest.raises(RuntimeError, match="peer memory is not available"):
+            sharding.PeerReducer(1000, torch.device("cuda", rank), None)
+        with pytest.raises(RuntimeError, match="needs a CUDA device"):
+            sharding.PeerReducer(1000, torch.device("cpu"), None)
+        t = torch.tensor([float(rank)])
+        dist.all_reduce(t)                         # the group is still usable afterwards
+        assert float(t) == float(sum(range(world)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_reducer_fails_together_without_peer_memory_world2_gloo():
+    mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
