@@ -7,7 +7,7 @@ Default workload (N=1): BASELINE config 2 -- FastGRNN KWS inference, input 32, h
 batch 8192 per GPU, full-rank W/U, fp32 state.  A "step" is one forward pass of the hot path over
 one batch of synthetic MFCC tensors.  N>1 (launched by torch.distributed.run, one rank per GPU):
 every rank runs its own 8192-row batch (weak scaling; no data-path collective for inference;
-workload c3 adds the NCCL gradient all-reduce).
+workload c3 adds the gradient all-reduce: our fused peer-memory all-reduce + SGD kernel, or NCCL with --collective nccl).
 
 `value`     = whole-job sequences/s with inputs resident in HBM (device-timed, max over ranks).
 `e2e`       = the same metric through kws_b200.streaming.HostPipeline with pinned HOST buffers,
@@ -16,7 +16,7 @@ workload c3 adds the NCCL gradient all-reduce).
 `cpu_baseline` / `--impl reference` = the CPU restatement of the reference rnn.py FastGRNN
               (oracle/, bit-identical to the reference in the build container) on the host cores.
 `extra`     = short runs of the other BASELINE configurations at the same N (c3: data-parallel training step with the
-              NCCL gradient all-reduce, c4: low rank H=256, c5: T=1000 bf16, m1/m2: the two layers of the reference's
+              gradient all-reduce -- `collective` says which one ran --, c4: low rank H=256, c5: T=1000 bf16, m1/m2: the two layers of the reference's
               default model), each with its own value / ms_per_step / roofline, so that the scaling record covers the
               path that has a collective.
 """
