@@ -1,4 +1,5 @@
 # flagship forward: TMA tile stores (shipped lib) against the scalar-store build (libfastgrnn_b200_vS.so), and 64- / 56- / 48-row CTAs
+# variant: make -C kws_b200/csrc variant TAG=vS DEFS="-DTC_TMA_STORE=0"   (TC_TMA_STORE=1: staging before the hand-off)
 L=/root/repo/kws_b200/lib
 O=gpurun_out/tcab; mkdir -p $O
 timeout 400 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
