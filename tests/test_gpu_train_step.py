@@ -123,3 +123,33 @@ def test_fused_step_matches_autograd_on_the_oracle(B, T, batch_first):
             assert torch.allclose(getattr(layer.cell, k).detach().cpu(), v.detach(), rtol=1e-5, atol=1e-6), (it, k)
     # the modules still see the flat buffer: inference after training uses the updated weights
     assert layer.cell.W.data_ptr() == step.flat_params.data_ptr()
+
+
+@pytest.mark.parametrize("n", [22415, 1001, 6])
+def test_peer_step_with_one_rank_is_the_flat_sgd_step(n):
+    """fgrnn_sgd_allreduce_peer at world size 1 (nothing to push, the sum is this rank's bucket) == fgrnn_sgd_flat bit for
+    bit, over several steps (both parities of the receive area, the kernel's own step counters), odd lengths included;
+    `reduced` receives the bucket.  The multi-rank exchange itself is checked by tests/dist_check.py under torchrun."""
+    import ctypes as C
+    from kws_b200 import _lib, engine, train_step
+    lib = _lib.load()
+    torch.manual_seed(n)
+    p0 = torch.randn(n, device=dev())
+    params, ref = p0.clone(), p0.clone()
+    reduced = torch.empty(n, device=dev())
+    recv = torch.zeros(int(lib.fgrnn_peer_recv_bytes(n, 1)) // 4, device=dev())
+    state = torch.zeros(int(lib.fgrnn_peer_state_bytes()) // 4, dtype=torch.int32, device=dev())
+    for step in range(3):
+        g = torch.randn(n, device=dev())
+        d = _lib.FgrnnPeerStep()
+        d.abi_version, d.device, d.world, d.rank = _lib.ABI_VERSION, dev().index or 0, 1, 0
+        d.params, d.reduced, d.bucket, d.state = params.data_ptr(), reduced.data_ptr(), g.data_ptr(), state.data_ptr()
+        d.recv[0] = recv.data_ptr()
+        d.n, d.lr, d.grad_scale = n, 0.05, 1.0
+        _lib.check(lib.fgrnn_sgd_allreduce_peer(C.byref(d), engine._stream(dev())), "sgd_allreduce_peer")
+        train_step.sgd_flat(ref, g, 0.05, 1.0)
+        torch.cuda.synchronize()
+        assert torch.equal(params, ref), step
+        assert torch.equal(reduced, g), step
+    grid = min(32, (((n + 1) // 2) + 255) // 256)
+    assert state[:grid].tolist() == [3] * grid and int(state[32]) == 0
