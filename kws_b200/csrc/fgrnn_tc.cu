@@ -23,7 +23,8 @@
 //   warps 0..15  : epilogue, 8 per sub-tile (4 TMEM lane quadrants x 2 row halves); thread = hidden unit, 16 rows:
 //                  tcgen05.ld CA, CB, M1, M2 -> sum -> gate update on the packed fp32x2 pipe, one MUFU.EX2 and one
 //                  MUFU.RCP per element, state h in registers for all T steps -> fp16 split -> 16-byte st.shared into
-//                  the MN-major operand tile -> fence.proxy.async -> mbarrier -> (then) STG h_t, 128 B per warp per row
+//                  the MN-major operand tile -> fence.proxy.async -> mbarrier -> (then) h_t into the warp's staging tile and out
+//                  through one TMA tile store per warp (TC_TMA_STORE; scalar STG, 128 B per warp per row, when compiled out)
 //   warps 16..19 : x path: TMA (cp.async.bulk.tensor, 3-D map over [B,T,I] by the caller's strides), 16 rows and a
 //                  private 4-stage raw ring per warp -> fp16 hi/lo split -> K-major operand tiles (4 buffers)
 //   warps 20..22 : MMA issuers: the 30 MMAs of a sub-tile step, 10 per warp, on one elected lane in a straight-line
